@@ -1,0 +1,45 @@
+/* libttt_b200.so -- C ABI of the B200-native TTT hot path (sm_100a).
+ *
+ * Drop-in boundary: these entry points are what the reference's native extension `test_time_training`
+ * (ttt-tk/test_time_training.cpp:25-105, pybind11) binds for this path, restated with plain device pointers and
+ * sizes instead of torch::Tensor.  All pointers are DEVICE pointers unless a name ends in `_host`.  Every function
+ * is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream), performs no device
+ * synchronisation (the reference blocks with cudaDeviceSynchronize, ttt-tk/kernels/ttt/ttt.cu:714-715), keeps no
+ * state between calls, and returns 0 on success or a cudaError_t / negative argument-error code; the message is
+ * available from ttt_b200_last_error().  Caller allocates everything (reference: mlp_tk.py:92-98,192-225).
+ *
+ * Tensor layouts (contiguous, row-major):
+ *   XQ, XK, XV, Out        bf16 [B, H, NC, CS, 64]        (ttt.cu:621-630 TORCH_CHECKs)
+ *   last_eta               bf16 [B, H, NC, CS]            (= eta[:, :, :, -1, :], mlp_tk.py:105)
+ *   ln_weight, ln_bias     f32  [H, 64]                   (ttt_norm_weight/bias as [1,H,1,64], mlp_tk.py:112-113)
+ *   TTT-MLP   W1 f32 [B,H,64,256]  b1 f32 [B,H,256]  W2 f32 [B,H,256,64]  b2 f32 [B,H,64]   (CS = 64)
+ *   checkpoints            f32  [B, H, K, ...] with K = ceil(NC / checkpoint_group_size): state ENTERING group k
+ */
+#ifndef TTT_B200_H
+#define TTT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ttt_b200_version(void);
+const char* ttt_b200_last_error(void);
+
+/* TTT-MLP forward scan.  Replaces test_time_training.ttt_forward (ttt-tk/test_time_training.cpp:25-42,
+ * ttt-tk/kernels/ttt/ttt.cu:594-721).  Argument order follows the reference (Q, K, V).
+ * W*_ckpt may be NULL (no checkpoints written); W*_last may be NULL (final state not exported; the reference never
+ * exports it -- it is the hand-off message of the sequence-sharded mode). */
+int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta,
+                         const float* ln_weight, const float* ln_bias,
+                         const float* W1, const float* b1, const float* W2, const float* b2,
+                         float* W1_ckpt, float* b1_ckpt, float* W2_ckpt, float* b2_ckpt,
+                         float* W1_last, float* b1_last, float* W2_last, float* b2_last,
+                         void* Out, int B, int H, int NC, int checkpoint_group_size, void* stream);
+
+/* Debug/self-test: D[128][N] = A[128][K] . Bm[K][N] through one tcgen05 CTA (see csrc/umma_selftest.cu). */
+int ttt_b200_debug_umma(int mode, const void* A_bf16, const void* B_bf16, float* D, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,43 @@
+"""Diagnostic runner for the GPU box: each probe in its own process (a trapped kernel poisons the CUDA context)."""
+import subprocess
+import sys
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROBES = {
+    "umma": """
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from test_gpu_umma import run_umma
+for mode, N, K in [(0,64,64),(0,128,64),(0,64,256),(3,64,64),(3,128,64),(2,64,64),(2,64,128),(1,64,64),(1,64,256)]:
+    try:
+        print('umma mode', mode, 'N', N, 'K', K, 'relmax', run_umma(mode, N, K), flush=True)
+    except Exception as e:
+        print('umma mode', mode, N, K, 'EXC', repr(e)[:300], flush=True); break
+""" % (ROOT, ROOT),
+    "fwd": """
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from test_gpu_mlp_forward import run_forward, oracle_forward
+for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,2,4,2),(2,3,7,3),(1,4,33,16)]:
+    d = O.make_inputs(B,H,NC,seed=10+NC)
+    qkve, out, ck, last = run_forward(d, G, want_last=True)
+    ref, rck, rlast = oracle_forward(qkve, d, G)
+    per = [O.rel_err(out[:,:,n].float().cpu(), ref[:,:,n]) for n in range(min(NC,4))]
+    print('fwd', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'per-step', per,
+          'ck', [O.rel_err(a.cpu(), b) for a,b in zip(ck, rck)], 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
+""" % (ROOT, ROOT),
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(PROBES)
+    for n in names:
+        print(f"=== probe {n}", flush=True)
+        try:
+            r = subprocess.run([sys.executable, "-c", PROBES[n]], timeout=300, capture_output=True, text=True)
+            print(r.stdout[-6000:])
+            if r.returncode != 0:
+                print("RC", r.returncode, r.stderr[-3000:])
+        except subprocess.TimeoutExpired as e:
+            print("TIMEOUT", (e.stdout or b"")[-3000:])

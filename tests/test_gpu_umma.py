@@ -1,0 +1,26 @@
+"""GPU: tcgen05 descriptor conventions (csrc/umma_selftest.cu) against torch fp32 matmul of the same bf16 operands."""
+import pytest
+import torch
+
+from ttt_video_dit_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run_umma(mode, N, K, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
+    Bm = torch.randn(K, N, generator=g).to(torch.bfloat16).cuda()
+    D = torch.zeros(128, N, device="cuda")
+    b_arg = Bm.t().contiguous() if mode == 3 else Bm
+    code = _lib.lib().ttt_b200_debug_umma(mode, _lib.ptr(A), _lib.ptr(b_arg), _lib.ptr(D), N, K, _lib.current_stream())
+    _lib.check(code, "ttt_b200_debug_umma")
+    torch.cuda.synchronize()
+    ref = A.float() @ Bm.float()
+    return float((D - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("mode,N,K", [(0, 64, 64), (0, 128, 64), (0, 64, 256), (1, 64, 64), (1, 64, 256),
+                                      (2, 64, 64), (2, 64, 128), (3, 64, 64), (3, 128, 64)])
+def test_umma_modes(mode, N, K):
+    assert run_umma(mode, N, K) < 1e-5

@@ -1,0 +1,91 @@
+"""CPU: the oracle restatement is pinned to outputs of the unmodified reference (tests/golden/*.pt, produced by
+oracle/make_golden.py in the build container).  No GPU, no /root/reference needed."""
+import os
+
+import pytest
+import torch
+
+from oracle import ttt_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def _check_inputs(d, fx):
+    for k, v in fx["in_checksum"].items():
+        assert abs(float(d[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), f"RNG drift in {k}"
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_mlp_eager_and_primal_match_reference(idx):
+    fx = _load("ttt_mlp_ref.pt")[idx]
+    c = fx["cfg"]
+    d = O.make_inputs(c["B"], c["H"], c["NC"], CS=64, Fd=64, seed=c["seed"], dtype=torch.float64)
+    _check_inputs(d, fx)
+    grads, out = O.ttt_mlp_eager_grads(d["XQ"], d["XK"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], d["dOut"])
+    assert O.rel_err(out, fx["out"]) < 1e-6
+    for g, r in zip(grads[:9], fx["grads"][:9]):
+        assert O.rel_err(g, r) < 1e-5
+    assert O.rel_err(grads[9].sum(-2), fx["grads"][9]) < 1e-5
+    # primal form == the reference (row-uniform eta), incl. the hand-derived backward
+    le = d["eta"][:, :, :, -1, :, None]
+    po, ck, last = O.ttt_mlp_primal_forward(d["XQ"], d["XK"], d["XV"], le, d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], 2)
+    assert O.rel_err(po, fx["out"]) < 1e-6
+    assert ck[0].shape[2] == (c["NC"] + 1) // 2
+    assert torch.equal(ck[0][:, :, 0], d["W1"])
+    pb = O.ttt_mlp_primal_backward(d["XQ"], d["XK"], d["XV"], le, d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], d["dOut"])
+    for n, r in zip(["dln_w", "dln_b", "dW1", "db1", "dW2", "db2", "dXQ", "dXV", "dXK"], fx["grads"][:9]):
+        assert O.rel_err(pb[n], r) < 1e-5, n
+    assert O.rel_err(pb["dlast_eta"].squeeze(-1), fx["grads"][9]) < 1e-5
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_linear_matches_reference(idx):
+    fx = _load("ttt_linear_ref.pt")[idx]
+    c = fx["cfg"]
+    d = O.make_inputs(c["B"], c["H"], c["NC"], CS=16, Fd=64, seed=c["seed"], dtype=torch.float64, base_lr=1.0, linear=True)
+    _check_inputs(d, fx)
+    grads, out = O.ttt_linear_eager_grads(d["XQ"], d["XK"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["dOut"])
+    assert O.rel_err(out, fx["out"]) < 1e-6
+    for g, r in zip(grads[:7], fx["grads"][:7]):
+        assert O.rel_err(g, r) < 1e-5
+    assert O.rel_err(grads[7].sum(-2), fx["grads"][7]) < 1e-5
+    le = d["eta"][:, :, :, -1, :, None]
+    po, _ = O.ttt_linear_primal_forward(d["XQ"], d["XK"], d["XV"], le, d["ln_w"], d["ln_b"], d["W1"], d["b1"])
+    assert O.rel_err(po, fx["out"]) < 1e-6
+
+
+def test_seq_block_gate_and_attention_match_reference():
+    fx = _load("seq_block_ref.pt")
+    c = fx["cfg"]
+    vid, txt = fx["vid"].double(), fx["txt"].double()
+    P = {k: v.double() for k, v in fx["P"].items()}
+    sin, cos = O.rope3d_tables(c["Hh"], c["Ww"], c["frames"], c["E"] // c["NH"])
+    a = O.local_attention_block(vid, txt, P, c["NH"], c["TL"], c["Hh"] * c["Ww"], c["chunks"], c["attn_length"], c["prefix"],
+                                sin.double(), cos.double(), c["ln_eps"])
+    assert O.rel_err(a, fx["attn_ref"]) < 1e-5
+
+    def stub(x):
+        return torch.cumsum(x, dim=1) * 0.01 + torch.roll(x, 1, dims=-1) * 0.5
+    al = {k: v.double() for k, v in fx["alphas"].items()}
+    emb = torch.cat((txt, vid), dim=1)
+    s = O.ssm_bidirectional(emb, stub, c["TL"] * c["chunks"], c["chunks"], True,
+                            al["forward_ssm_gating_text.gating_alpha"], al["forward_ssm_gating_video.gating_alpha"],
+                            al["backward_ssm_gating_text.gating_alpha"], al["backward_ssm_gating_video.gating_alpha"])
+    assert O.rel_err(s, fx["ssm_ref"]) < 1e-5
+
+
+def test_dual_equals_primal_only_for_row_uniform_eta():
+    """SURVEY parity trap #1: with row-non-uniform eta the eager dual form and the last-row primal form differ."""
+    d = O.make_inputs(1, 2, 2, seed=5, dtype=torch.float64)
+    le = d["eta"][:, :, :, -1, :, None]
+    e, _ = O.ttt_mlp_eager(d["XK"], d["XQ"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"])
+    p, _, _ = O.ttt_mlp_primal_forward(d["XQ"], d["XK"], d["XV"], le, d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], 1)
+    assert O.rel_err(p, e.permute(0, 3, 1, 2, 4)) < 1e-12
+    eta2 = d["eta"].clone()
+    eta2[:, :, :, :32] *= 3.0  # rows differ
+    e2, _ = O.ttt_mlp_eager(d["XK"], d["XQ"], d["XV"], eta2, d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"])
+    assert O.rel_err(p, e2.permute(0, 3, 1, 2, 4)) > 1e-6

@@ -1,0 +1,57 @@
+"""ctypes binding of libttt_b200.so (C-ABI in include/ttt_b200.h).  No fallback: if the library is missing or a call
+fails this raises -- the product path never routes through torch eager or the oracle."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libttt_b200.so")
+_lib = None
+
+_vp, _fp, _i = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
+
+_SIGS = {
+    "ttt_b200_version": ([], ctypes.c_int),
+    "ttt_b200_last_error": ([], ctypes.c_char_p),
+    "ttt_b200_mlp_forward": ([_vp] * 4 + [_fp] * 2 + [_fp] * 4 + [_fp] * 4 + [_fp] * 4 + [_vp] + [_i] * 4 + [_vp], ctypes.c_int),
+    "ttt_b200_debug_umma": ([_i, _vp, _vp, _fp, _i, _i, _vp], ctypes.c_int),
+}
+
+
+class TTTB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TTTB200Error(
+                f"{LIB_PATH} not found: build it with `python ttt-video-dit_b200/build.py` "
+                "(there is no CPU / eager fallback for this path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError if the ABI symbol is missing
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().ttt_b200_last_error()
+        raise TTTB200Error(f"{what} failed with code {code}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

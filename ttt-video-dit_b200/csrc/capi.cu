@@ -1,0 +1,48 @@
+// extern "C" surface of libttt_b200.so (declared in include/ttt_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ttt_b200.h"
+#include "ttt_internal.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+static int cuda_ret(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+  return (int)e;
+}
+
+extern "C" {
+
+int ttt_b200_version(void) { return 100; }
+const char* ttt_b200_last_error(void) { return g_err; }
+
+int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_weight,
+                         const float* ln_bias, const float* W1, const float* b1, const float* W2, const float* b2,
+                         float* W1_ckpt, float* b1_ckpt, float* W2_ckpt, float* b2_ckpt, float* W1_last,
+                         float* b1_last, float* W2_last, float* b2_last, void* Out, int B, int H, int NC,
+                         int checkpoint_group_size, void* stream) {
+  if (!XQ || !XK || !XV || !last_eta || !ln_weight || !ln_bias || !W1 || !b1 || !W2 || !b2 || !Out)
+    return fail(-1, "ttt_b200_mlp_forward: null pointer argument");
+  if (B <= 0 || H <= 0 || NC <= 0 || checkpoint_group_size <= 0)
+    return fail(-2, "ttt_b200_mlp_forward: B, H, NC and checkpoint_group_size must be positive");
+  const bool any_ck = W1_ckpt || b1_ckpt || W2_ckpt || b2_ckpt, all_ck = W1_ckpt && b1_ckpt && W2_ckpt && b2_ckpt;
+  if (any_ck && !all_ck) return fail(-3, "ttt_b200_mlp_forward: checkpoint buffers must be all set or all NULL");
+  const bool any_l = W1_last || b1_last || W2_last || b2_last, all_l = W1_last && b1_last && W2_last && b2_last;
+  if (any_l && !all_l) return fail(-3, "ttt_b200_mlp_forward: final-state buffers must be all set or all NULL");
+  return cuda_ret(tb::launch_mlp_forward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1, b1, W2, b2, W1_ckpt, b1_ckpt,
+                                         W2_ckpt, b2_ckpt, W1_last, b1_last, W2_last, b2_last, Out, B, H, NC,
+                                         checkpoint_group_size, (cudaStream_t)stream),
+                  "ttt_b200_mlp_forward");
+}
+
+int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N, int K, void* stream) {
+  return cuda_ret(tb::launch_umma_selftest(mode, A, Bm, D, N, K, (cudaStream_t)stream), "ttt_b200_debug_umma");
+}
+
+}  // extern "C"

@@ -1,0 +1,540 @@
+// TTT-MLP forward scan for sm_100a (tcgen05 + TMEM + TMA).  One CTA per (batch, head) sequence.
+//
+// Replaces ttt-tk/kernels/ttt/ttt.cu:85-721 (fwd_ttt_mlp_ker / ttt_forward, Hopper wgmma) with a Blackwell design;
+// the arithmetic it must reproduce is the reference's eager step ttt/models/ssm/ops/ttt_mlp.py:9-67 in its primal
+// form, LayerNorm eps 1e-8 (ttt/models/ssm/ops/utils.py:4,21).
+//
+// Layout idea ("hidden units on TMEM lanes"): every 256-wide tensor is kept transposed so that the MMA M dimension is
+// the 4F=256 hidden dimension (2 x M=128, full-rate tcgen05) and each thread owns one hidden unit:
+//   W1^T [256 x 64] fp32 and W2 [256 x 64] fp32 are *persistent TMEM accumulators*; the TTT update
+//   W -= (eta*X)^T grad is an accumulate-MMA, the master copy never leaves TMEM.
+//   D1   = W1b^T . [K_t | Q_{t-1}]^T   -> [256 hidden x 128 tokens]   (Z1_t^T and Zbar1_{t-1}^T in ONE MMA batch)
+//   D2   = [X2_t ; X2bar_{t-1}] . W2b  -> [128 tokens x 64]           (Z2_t and Zbar2_{t-1}, M=128 full rate)
+//   D3   = W2b . G2^T                  -> [256 x 64 tokens]           (-eta * gradZ2 W2^T)
+//   W2  += X2^T . G2 ;  W1^T += G1^T . K                               (G = -eta*grad, bf16)
+// The Q side of mini-batch t-1 rides along with the K side of mini-batch t (software pipelining by one step), which
+// makes both "half-size" GEMMs of the recurrence M=128.  bf16 operand copies of W (W1b^T, W2b) are re-materialised
+// from TMEM once per step.  All smem operand tiles use the SW128 row-tile convention of ptx.cuh.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+#include "ttt_internal.h"
+
+namespace tb {
+
+constexpr int CS = 64, F = 64, HID = 256;
+constexpr int NT = 256;
+
+// shared memory map (bytes)
+constexpr uint32_t SM_W1B = 0;                    // W1^T bf16 [256][64]   (A, K-major, K = F)
+constexpr uint32_t SM_W2B = 32768;                // W2   bf16 [256][64]   (A K-major for D3; B MN-major for D2)
+constexpr uint32_t SM_X2 = 65536;                 // block0: X2^T [256][64 tok] ; block1: X2bar^T (later reused for G1^T)
+constexpr uint32_t SM_KQ = 131072;                // 2 slots x { K_t [64][64] ; Q_{t-1} [64][64] }
+constexpr uint32_t SM_V = SM_KQ + 2 * 16384;      // 2 slots x V_t [64][64]
+constexpr uint32_t SM_G2 = SM_V + 2 * 8192;       // G2 = -eta*gradZ2 bf16 [64 tok][64]
+constexpr uint32_t SM_MISC = SM_G2 + 8192;        // b2[64] f32, ln_w[64], ln_b[64], barriers, tmem ptr
+constexpr uint32_t SM_TOTAL = SM_MISC + 1024;
+
+// TMEM column map (512 columns allocated)
+constexpr uint32_t TM_W1 = 0;    // + 64*h
+constexpr uint32_t TM_W2 = 128;  // + 64*h
+constexpr uint32_t TM_D1 = 256;  // + 128*h ; cols [0,64) K side, [64,128) Q side
+constexpr uint32_t TM_D3 = 256;  // + 128*h ; aliases the K side of D1
+constexpr uint32_t TM_D2 = 320;  // aliases the Q side of D1 half 0
+
+__device__ __forceinline__ float gelu_and_grad(float z, float& grad) {
+  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
+  float z2 = z * z;
+  float u = z * fmaf(c1, z2, c0);
+  float t = tanh_fast(u);
+  float hz = 0.5f * z;
+  // ops/utils.py:51-54: 0.5*x*((1-t^2)*(0.79788456+0.1070322243*x^2)) + 0.5*(1+t)
+  grad = fmaf(hz * fmaf(-t, t, 1.0f), fmaf(3.0f * c1, z2, c0), fmaf(0.5f, t, 0.5f));
+  return fmaf(hz, t, hz);
+}
+__device__ __forceinline__ float gelu_only(float z) {
+  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
+  float u = z * fmaf(c1, z * z, c0);
+  float t = tanh_fast(u);
+  float hz = 0.5f * z;
+  return fmaf(hz, t, hz);
+}
+
+struct FwdParams {
+  const __nv_bfloat16* last_eta;  // [B,H,NC,64]
+  const float* ln_w;              // [H,64]
+  const float* ln_b;
+  const float *W1, *b1, *W2, *b2;      // initial state [B,H,64,256],[B,H,256],[B,H,256,64],[B,H,64]
+  float *W1c, *b1c, *W2c, *b2c;        // checkpoints [B,H,K,...] (may be null)
+  float *W1o, *b1o, *W2o, *b2o;        // final state (may be null)
+  __nv_bfloat16* Out;                  // [B,H,NC,64,64]
+  int B, H, NC, ckpt_group, K;
+};
+
+// store one thread's state rows (fp32, still in registers) to a [64][256] W1 image and a [256][64] W2 image
+__device__ __forceinline__ void store_w1_col(float* W1g, int j, const uint32_t* v, int f0) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) W1g[(size_t)(f0 + i) * HID + j] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void store_w2_row(float* W2g, int j, const uint32_t* v, int f0) {
+  float4* dst = reinterpret_cast<float4*>(W2g + (size_t)j * F + f0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                         __uint_as_float(v[4 * i + 3]));
+}
+// 32 fp32 (registers) -> bf16 -> 4 chunks of a SW128 row
+__device__ __forceinline__ void store_row_bf16(uint32_t tile_saddr, int row, int chunk0, const uint32_t* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t p0 = pack_bf16(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
+    uint32_t p1 = pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+    uint32_t p2 = pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+    uint32_t p3 = pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+    st_shared_v4(tile_saddr + sw128_off(row, chunk0 + c), p0, p1, p2, p3);
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x;
+  const int head = bh % p.H;
+  const int NC = p.NC;
+
+  float* b2s = reinterpret_cast<float*>(smem + SM_MISC);
+  float* lnw = b2s + 64;
+  float* lnb = lnw + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC + 768);
+  uint64_t* tma_bar = bars;      // [2]
+  uint64_t* mma_bar = bars + 2;  // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  if (tid == 0) {
+    mbar_init(&tma_bar[0], 1);
+    mbar_init(&tma_bar[1], 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  if (tid < 64) {
+    lnw[tid] = p.ln_w[head * 64 + tid];
+    lnb[tid] = p.ln_b[head * 64 + tid];
+    b2s[tid] = p.b2[(size_t)bh * 64 + tid];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const int half = warp >> 2;                                    // which 128-row half of the hidden dim
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;  // this warp's TMEM lane quarter
+  const int j = tid;                                             // hidden unit owned by this thread (P2/P6/P8)
+  const size_t row_base = (size_t)bh * NC * CS;                   // first token row of this sequence in [B*H*NC*CS, 64]
+
+  // prologue TMA: K_0, V_0 into slot 0
+  if (tid == 0) {
+    mbar_expect_tx(&tma_bar[0], 16384);
+    tma_load_2d(smem + SM_KQ, &tmK, 0, (int)row_base, &tma_bar[0]);
+    tma_load_2d(smem + SM_V, &tmV, 0, (int)row_base, &tma_bar[0]);
+  }
+
+  // ---- initial state: global fp32 -> TMEM accumulators + bf16 operand copies (+ checkpoint 0)
+  float b1r = p.b1[(size_t)bh * HID + j];
+  {
+    const float* W1g = p.W1 + (size_t)bh * F * HID;
+    const float* W2g = p.W2 + (size_t)bh * HID * F;
+    uint32_t v[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(W1g[(size_t)(32 * c + i) * HID + j]);
+      tmem_st32(tmem + lane_addr + TM_W1 + 64 * half + 32 * c, v);
+      store_row_bf16(sbase + SM_W1B, j, 4 * c, v);
+      if (p.W1c) store_w1_col(p.W1c + ((size_t)bh * p.K) * F * HID, j, v, 32 * c);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(W2g[(size_t)j * F + 32 * c + i]);
+      tmem_st32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
+      store_row_bf16(sbase + SM_W2B, j, 4 * c, v);
+      if (p.W2c) store_w2_row(p.W2c + ((size_t)bh * p.K) * HID * F, j, v, 32 * c);
+    }
+    if (p.b1c) p.b1c[((size_t)bh * p.K) * HID + j] = b1r;
+    if (p.b2c && tid < 64) p.b2c[((size_t)bh * p.K) * F + tid] = p.b2[(size_t)bh * 64 + tid];
+    tc_wait_st();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  constexpr uint32_t IDESC_A = make_idesc_bf16(128, 128, false, false);  // D1: A K-major, B K-major
+  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true);     // D2: A MN-major, B MN-major
+  constexpr uint32_t IDESC_C = make_idesc_bf16(128, 64, false, false);   // D3
+  constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
+
+  uint32_t mma_phase = 0;
+  uint32_t gp[32];  // gelu'(Z1) for this thread's hidden unit, 64 tokens, packed bf16x2
+
+  for (int it = 0; it <= NC; ++it) {
+    const int slot = it & 1;
+    const bool has_k = it < NC, has_q = it > 0;
+    const uint32_t kq = sbase + SM_KQ + slot * 16384;
+    const uint32_t vt = sbase + SM_V + slot * 8192;
+
+    // prefetch eta for the LN threads of the K side
+    float eta_i = 0.f;
+    if (has_k && warp < 2) eta_i = __bfloat162float(p.last_eta[((size_t)bh * NC + it) * CS + tid]);
+
+    mbar_wait(&tma_bar[slot], (it >> 1) & 1);
+    if (tid == 0 && it < NC) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
+      const int ns = slot ^ 1;
+      const bool nk = (it + 1) < NC;
+      mbar_expect_tx(&tma_bar[ns], nk ? 24576 : 8192);
+      if (nk) {
+        tma_load_2d(smem + SM_KQ + ns * 16384, &tmK, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
+        tma_load_2d(smem + SM_V + ns * 8192, &tmV, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
+      }
+      tma_load_2d(smem + SM_KQ + ns * 16384 + 8192, &tmQ, 0, (int)(row_base + (size_t)it * CS), &tma_bar[ns]);
+    }
+
+    // ---------------- P1: D1[h] = W1b^T[h] . [K | Q]^T   (M=128, N=128, K=64)
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t da = make_desc_sw128(sbase + SM_W1B + h * 16384, 16, 1024);
+        const uint64_t db = make_desc_sw128(kq, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), IDESC_A, k > 0);
+      }
+      tc_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+
+    // ---------------- P2: gelu on D1 row j -> X2^T / X2bar^T (bf16, SW128 rows); keep gelu'(Z1)
+    {
+      const uint32_t tsrc = tmem + lane_addr + TM_D1 + 128 * half;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if ((c < 2 && !has_k) || (c >= 2 && !has_q)) continue;
+        uint32_t v[32];
+        tmem_ld32(tsrc + 32 * c, v);
+        tc_wait_ld();
+        if (c < 2) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float g0, g1;
+            float x0 = gelu_and_grad(__uint_as_float(v[i]) + b1r, g0);
+            float x1 = gelu_and_grad(__uint_as_float(v[i + 1]) + b1r, g1);
+            v[i] = __float_as_uint(x0);
+            v[i + 1] = __float_as_uint(x1);
+            gp[16 * c + i / 2] = pack_bf16(g0, g1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_only(__uint_as_float(v[i]) + b1r));
+        }
+        store_row_bf16(sbase + SM_X2 + (c >> 1) * 32768, j, 4 * (c & 1), v);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- P3: D2 = [X2 ; X2bar] . W2b   (M=128 tokens, N=64, K=256 hidden; both operands MN-major)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t da = make_desc_sw128(sbase + SM_X2, 32768, 1024);
+      const uint64_t db = make_desc_sw128(sbase + SM_W2B, 1024, 1024);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        umma_ss(tmem + TM_D2, desc_advance(da, 2048 * k), desc_advance(db, 2048 * k), IDESC_B, k > 0);
+      tc_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+
+    // ---------------- P4: LayerNorm stage, one token row per thread (warps 0-3 own TMEM lanes 0-127)
+    if (warp < 4) {
+      const int row = tid;  // 0..63 K side, 64..127 Q side
+      const bool kside = row < 64;
+      if ((kside && has_k) || (!kside && has_q)) {
+        float z[64];
+        {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_addr + TM_D2, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(v[i]) + b2s[i];
+          tmem_ld32(tmem + lane_addr + TM_D2 + 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) z[32 + i] = __uint_as_float(v[i]) + b2s[32 + i];
+        }
+        float mu = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mu += z[i];
+        mu *= (1.0f / 64.0f);
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          z[i] -= mu;
+          var = fmaf(z[i], z[i], var);
+        }
+        var *= (1.0f / 64.0f);
+        const float rstd = rsqrtf(var + 1e-8f);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) z[i] *= rstd;  // x_hat
+        if (kside) {
+          // grad_out = gamma*xhat + beta - (V - K); gxh = grad_out*gamma
+          const int r = row;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t kk[4], vv[4];
+            ld_shared_v4(kq + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
+            ld_shared_v4(vt + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int f = 8 * c + 2 * e;
+              float t0 = bf16_lo(vv[e]) - bf16_lo(kk[e]);
+              float t1 = bf16_hi(vv[e]) - bf16_hi(kk[e]);
+              float g0 = (fmaf(lnw[f], z[f], lnb[f]) - t0) * lnw[f];
+              float g1 = (fmaf(lnw[f + 1], z[f + 1], lnb[f + 1]) - t1) * lnw[f + 1];
+              s1 += g0 + g1;
+              s2 = fmaf(g0, z[f], s2);
+              s2 = fmaf(g1, z[f + 1], s2);
+              // stash gxh in place of nothing: recompute below needs z and g -> keep g in a second pass
+              // (registers: store g over kk/vv is not possible; we recompute g in pass 2)
+            }
+          }
+          // pass 2: gradZ2 = (64*g - s1 - xhat*s2) / (64*std);  G2 = -eta * gradZ2
+          const float sc = -eta_i * rstd * (1.0f / 64.0f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t kk[4], vv[4], o[4];
+            ld_shared_v4(kq + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
+            ld_shared_v4(vt + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int f = 8 * c + 2 * e;
+              float t0 = bf16_lo(vv[e]) - bf16_lo(kk[e]);
+              float t1 = bf16_hi(vv[e]) - bf16_hi(kk[e]);
+              float g0 = (fmaf(lnw[f], z[f], lnb[f]) - t0) * lnw[f];
+              float g1 = (fmaf(lnw[f + 1], z[f + 1], lnb[f + 1]) - t1) * lnw[f + 1];
+              float d0 = (fmaf(64.0f, g0, -s1) - z[f] * s2) * sc;
+              float d1 = (fmaf(64.0f, g1, -s1) - z[f + 1] * s2) * sc;
+              o[e] = pack_bf16(d0, d1);
+            }
+            st_shared_v4(sbase + SM_G2 + sw128_off(r, c), o[0], o[1], o[2], o[3]);
+          }
+        } else {
+          // output: O = Q + gamma*xhat + beta   (mini-batch it-1)
+          const int r = row - 64;
+          __nv_bfloat16* og = p.Out + (row_base + (size_t)(it - 1) * CS + r) * F;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t qq[4], o[4];
+            ld_shared_v4(kq + 8192 + sw128_off(r, c), qq[0], qq[1], qq[2], qq[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int f = 8 * c + 2 * e;
+              float o0 = bf16_lo(qq[e]) + fmaf(lnw[f], z[f], lnb[f]);
+              float o1 = bf16_hi(qq[e]) + fmaf(lnw[f + 1], z[f + 1], lnb[f + 1]);
+              o[e] = pack_bf16(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(og + 8 * c) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+    if (!has_k) break;  // last iteration only drains the Q side
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- P5: D3[h] = W2b[h] . G2^T  (critical) ;  W2[h] += X2^T[h] . G2  (off the critical path)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t dg_k = make_desc_sw128(sbase + SM_G2, 16, 1024);     // B K-major view  (N = token, K = F)
+      const uint64_t dg_mn = make_desc_sw128(sbase + SM_G2, 1024, 1024);  // B MN-major view (K = token, N = F)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t da = make_desc_sw128(sbase + SM_W2B + h * 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + TM_D3 + 128 * h, desc_advance(da, 32 * k), desc_advance(dg_k, 32 * k), IDESC_C, k > 0);
+      }
+      tc_commit(mma_bar);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t da = make_desc_sw128(sbase + SM_X2 + h * 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + TM_W2 + 64 * h, desc_advance(da, 32 * k), desc_advance(dg_mn, 2048 * k), IDESC_U, 1);
+      }
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+
+    // ---------------- P6: G1^T row j = D3 row j * gelu'(Z1) (bf16) ; b1 += sum ; threads 0-63: b2 += column sums of G2
+    {
+      const uint32_t tsrc = tmem + lane_addr + TM_D3 + 128 * half;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tsrc + 32 * c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a0 = __uint_as_float(v[i]) * bf16_lo(gp[16 * c + i / 2]);
+          float a1 = __uint_as_float(v[i + 1]) * bf16_hi(gp[16 * c + i / 2]);
+          acc += a0 + a1;
+          v[i] = __float_as_uint(a0);
+          v[i + 1] = __float_as_uint(a1);
+        }
+        store_row_bf16(sbase + SM_X2 + 32768, j, 4 * c, v);
+      }
+      b1r += acc;
+      if (tid < 64) {
+        float s = 0.f;
+        const int f = tid;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) {
+          const __nv_bfloat16* rowp = reinterpret_cast<const __nv_bfloat16*>(smem + SM_G2 + sw128_off(i, f >> 3));
+          s += __bfloat162float(rowp[f & 7]);
+        }
+        b2s[f] += s;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- P7: W1^T[h] += G1^T[h] . K
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t db = make_desc_sw128(kq, 1024, 1024);  // K tile, MN-major view (K = token, N = F)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t da = make_desc_sw128(sbase + SM_X2 + 32768 + h * 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + TM_W1 + 64 * h, desc_advance(da, 32 * k), desc_advance(db, 2048 * k), IDESC_U, 1);
+      }
+      tc_commit(mma_bar);  // also covers the W2 update issued in P5
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+
+    // ---------------- P8: re-materialise bf16 operand copies of the new state (+ checkpoint / final state)
+    {
+      const int nstep = it + 1;  // state now equals the state entering mini-batch nstep
+      const bool ck = (p.W1c != nullptr) && (nstep < NC) && (nstep % p.ckpt_group == 0);
+      const bool fin = (p.W1o != nullptr) && (nstep == NC);
+      const size_t kidx = ck ? ((size_t)bh * p.K + nstep / p.ckpt_group) : 0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + TM_W1 + 64 * half + 32 * c, v);
+        tc_wait_ld();
+        store_row_bf16(sbase + SM_W1B, j, 4 * c, v);
+        if (ck) store_w1_col(p.W1c + kidx * F * HID, j, v, 32 * c);
+        if (fin) store_w1_col(p.W1o + (size_t)bh * F * HID, j, v, 32 * c);
+        tmem_ld32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
+        tc_wait_ld();
+        store_row_bf16(sbase + SM_W2B, j, 4 * c, v);
+        if (ck) store_w2_row(p.W2c + kidx * HID * F, j, v, 32 * c);
+        if (fin) store_w2_row(p.W2o + (size_t)bh * HID * F, j, v, 32 * c);
+      }
+      if (ck) {
+        p.b1c[kidx * HID + j] = b1r;
+        if (tid < 64) p.b2c[kidx * F + tid] = b2s[tid];  // b2s was updated by the same thread in P6
+      }
+      if (fin) {
+        p.b1o[(size_t)bh * HID + j] = b1r;
+        if (tid < 64) p.b2o[(size_t)bh * F + tid] = b2s[tid];
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][64], box [64 rows][64 cols], 128-B swizzle
+int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {64, rows};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                               const float* ln_b, const float* W1, const float* b1, const float* W2, const float* b2,
+                               float* W1c, float* b1c, float* W2c, float* b2c, float* W1o, float* b1o, float* W2o,
+                               float* b2o, void* Out, int B, int H, int NC, int ckpt_group, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || NC <= 0 || ckpt_group <= 0) return cudaErrorInvalidValue;
+  CUtensorMap tq, tk, tv;
+  const uint64_t rows = (uint64_t)B * H * NC * CS;
+  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+  if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
+    return cudaErrorInvalidValue;
+  FwdParams p;
+  p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
+  p.ln_w = ln_w; p.ln_b = ln_b;
+  p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+  p.W1c = W1c; p.b1c = b1c; p.W2c = W2c; p.b2c = b2c;
+  p.W1o = W1o; p.b1o = b1o; p.W2o = W2o; p.b2o = b2o;
+  p.Out = reinterpret_cast<__nv_bfloat16*>(Out);
+  p.B = B; p.H = H; p.NC = NC; p.ckpt_group = ckpt_group;
+  p.K = (NC + ckpt_group - 1) / ckpt_group;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  ttt_mlp_fwd_kernel<<<B * H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+
+}  // namespace tb

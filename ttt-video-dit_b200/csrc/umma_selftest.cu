@@ -1,0 +1,104 @@
+// Self-test of the tcgen05 / descriptor conventions of ptx.cuh: one CTA computes D[128][N] = A[128][K] . B[K][N]
+// with the operand storage forms used by the TTT kernels.  Exposed through the C-ABI as ttt_b200_debug_umma so the
+// GPU test-suite can pin every (major-ness, N, K) combination independently of the big kernels.
+//   mode 0: A K-major,  B K-major   (any N multiple of 16 <= 128, K multiple of 64)
+//   mode 1: A MN-major (two 64-row blocks, LBO = K*128), B MN-major (N = 64)
+//   mode 2: A K-major,  B MN-major  (N = 64)
+//   mode 3: as mode 0 with K = 64 but B [N][64] is fetched by TMA (SWIZZLE_128B tensor map) instead of st.shared
+#include "ptx.cuh"
+#include "ttt_internal.h"
+
+namespace tb {
+
+__device__ __forceinline__ uint32_t elem_off(int r, int col) { return sw128_off(r, col >> 3) + (uint32_t)(col & 7) * 2u; }
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __nv_bfloat16* __restrict__ A,
+                     const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t a_bytes = 128u * (uint32_t)K * 2u;
+  uint8_t* smB = smem + a_bytes;
+  const uint32_t sB = sA + a_bytes;
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<128>(&tmem_ptr);
+
+  // stage A
+  for (int idx = tid; idx < 128 * K; idx += 128) {
+    const int m = idx / K, k = idx % K;
+    uint32_t off;
+    if (mode == 1) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
+    else           off = (uint32_t)(k >> 6) * 16384u + elem_off(m, k & 63);
+    *reinterpret_cast<__nv_bfloat16*>(smem + off) = A[idx];
+  }
+  // stage B (logical Bm[k][n])
+  if (mode != 3) {
+    for (int idx = tid; idx < K * N; idx += 128) {
+      const int k = idx / N, n = idx % N;
+      uint32_t off;
+      if (mode == 0) off = (uint32_t)(k >> 6) * (uint32_t)N * 128u + elem_off(n, k & 63);
+      else           off = elem_off(k, n);
+      *reinterpret_cast<__nv_bfloat16*>(smB + off) = Bm[idx];
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (mode == 3 && tid == 0) {
+    mbar_expect_tx(&bar[1], (uint32_t)N * 128u);
+    for (int r = 0; r < N; r += 64) tma_load_2d(smB + r * 128, &tmB, 0, r, &bar[1]);
+  }
+  if (mode == 3) mbar_wait(&bar[1], 0);
+  const uint32_t tmem = tmem_ptr;
+
+  if (tid == 0) {
+    const bool a_mn = (mode == 1), b_mn = (mode == 1 || mode == 2);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
+    for (int k16 = 0; k16 < K / 16; ++k16) {
+      uint64_t da, db;
+      if (a_mn) da = desc_advance(make_desc_sw128(sA, (uint32_t)K * 128u, 1024), 2048u * k16);
+      else      da = desc_advance(make_desc_sw128(sA + (k16 >> 2) * 16384u, 16, 1024), 32u * (k16 & 3));
+      if (b_mn) db = desc_advance(make_desc_sw128(sB, 1024, 1024), 2048u * k16);
+      else      db = desc_advance(make_desc_sw128(sB + (k16 >> 2) * (uint32_t)N * 128u, 16, 1024), 32u * (k16 & 3));
+      umma_ss(tmem, da, db, idesc, k16 > 0);
+    }
+    tc_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tc_fence_after();
+  for (int c = 0; c < N; c += 8) {
+    uint32_t v[8];
+    tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tc_wait_ld();
+    for (int i = 0; i < 8; ++i) D[(size_t)tid * N + c + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float* D, int N, int K, cudaStream_t stream) {
+  if (mode < 0 || mode > 3 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
+  if ((mode == 1 || mode == 2) && N != 64) return cudaErrorInvalidValue;
+  if (mode == 3 && K != 64) return cudaErrorInvalidValue;
+  CUtensorMap tm;
+  // mode 3: Bm is given K-major already ([N][64] bf16); other modes do not dereference the map but it must be valid
+  if (make_token_tmap(&tm, mode == 3 ? Bm : A, mode == 3 ? (uint64_t)N : 128ull)) return cudaErrorInvalidValue;
+  const size_t smem = 128 * (size_t)K * 2 + (size_t)((mode == 0 || mode == 3) ? N * K * 2 : K * 128);
+  cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  umma_selftest_kernel<<<1, 128, smem, stream>>>(tm, mode, reinterpret_cast<const __nv_bfloat16*>(A),
+                                                 reinterpret_cast<const __nv_bfloat16*>(Bm), D, N, K);
+  return cudaGetLastError();
+}
+
+}  // namespace tb
