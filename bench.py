@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- TTT hot path benchmark (contract: see task statement / DESIGN.md "Measurement").
+
+A *step* is one pass of the TTT-MLP op over one batch of synthetic token tensors of the named shape:
+forward scan (+ backward scan when --mode fwdbwd) for ONE layer-direction of CogVideoX-5B
+(48 heads x 64, mini-batch 64).  Default workload = BASELINE.json configs[1]:
+3-second video, L = 18 048 tokens -> NC = 282 mini-batches, B = 1 per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fwd|fwdbwd] [--nc 282] [--batch 1]
+    python bench.py --impl reference ...      # the reference's eager CPU path (oracle port) on the host cores
+
+value   = tokens/s with inputs resident in HBM (CUDA-event time, max over ranks, whole-job aggregate)
+e2e     = same through the public op with HOST (pinned) inputs: H2D of q,k,v,eta + op + D2H of the result per step
+roofline= algorithmic TTT FLOPs (7U fwd, +15U bwd per head per mini-batch, U = 2*64*64*256) / kernel time vs
+          MEASURED_PEAKS.json bf16 peak
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+
+U_FLOP = 2 * 64 * 64 * 256
+FWD_U, BWD_U = 7, 15
+H_5B = 48
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "fwd", "fwdbwd"])
+    ap.add_argument("--nc", type=int, default=282, help="mini-batches per sequence (282 = 3 s, 804 = 9 s, 5487 = 63 s)")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--heads", type=int, default=H_5B)
+    ap.add_argument("--ckpt", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_eager_tokens_per_s(heads, mode, sample_nc=3, reps=1):
+    """The reference's eager path (oracle port of ttt/models/ssm/ops/ttt_mlp.py) on the host cores, fp32,
+    on a bounded prefix of the same workload; the scan cost is exactly linear in NC."""
+    import torch
+    from oracle import ttt_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    d = O.make_inputs(1, heads, sample_nc, seed=0)
+    best = None
+    for _ in range(reps + 1):  # first is warm-up
+        t0 = time.perf_counter()
+        if mode == "fwd":
+            with torch.no_grad():
+                O.ttt_mlp_eager(d["XK"], d["XQ"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"])
+        else:
+            O.ttt_mlp_eager_grads(d["XQ"], d["XK"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], d["dOut"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None or _ > 0 and dt < best else best
+    return sample_nc * 64 / best, best, f"{sample_nc} of the mini-batches x {heads} heads, fp32 eager dual form, {'fwd' if mode == 'fwd' else 'fwd+autograd bwd'}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mode = "fwdbwd" if args.mode in ("auto", "fwdbwd") else "fwd"
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, dt, sample = cpu_eager_tokens_per_s(args.heads, mode, sample_nc=2, reps=0)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    tok_s = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "video-tokens/sec TTT-MLP layer-direction (fwd+bwd)" if mode == "fwdbwd" else "video-tokens/sec TTT-MLP layer-direction (fwd)",
+        "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CogVideoX-5B TTT-MLP op, {args.heads} heads x 64, mini-batch 64, NC={args.nc} (sampled)", "mode": mode},
+        "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from oracle import ttt_oracle as O  # only for synthetic input generation + the cpu_baseline leg
+    from ttt_video_dit_b200 import mlp_tk
+
+    have_bwd = mlp_tk.HAVE_BACKWARD
+    mode = args.mode if args.mode != "auto" else ("fwdbwd" if have_bwd else "fwd")
+    if mode == "fwdbwd" and not have_bwd:
+        raise SystemExit("backward kernel not built")
+    B, H, NC, G = args.batch, args.heads, args.nc, args.ckpt
+    L = NC * 64
+
+    # synthetic inputs, generated once on the host, kept pinned for the e2e leg
+    gen = torch.Generator().manual_seed(1234 + rank)
+    rn = lambda *s: torch.randn(*s, generator=gen)
+    XQ = torch.nn.functional.normalize(rn(B, H, NC, 64, 64), dim=-1).to(torch.bfloat16).pin_memory()
+    XK = torch.nn.functional.normalize(rn(B, H, NC, 64, 64), dim=-1).to(torch.bfloat16).pin_memory()
+    XV = rn(B, H, NC, 64, 64).to(torch.bfloat16).pin_memory()
+    eta_last = ((0.1 / 64) * torch.sigmoid(rn(B, H, NC, 1, 64)) / 64).to(torch.bfloat16).pin_memory()  # one row of eta
+    dOut = rn(B, H, NC, 64, 64).to(torch.bfloat16).pin_memory()
+    ln_w = (1 + 0.1 * rn(H, 64)).to(dev)
+    ln_b = (0.1 * rn(H, 64)).to(dev)
+    W1 = (0.02 * rn(H, 64, 256)).unsqueeze(0).repeat(B, 1, 1, 1).to(dev)
+    b1 = torch.zeros(B, H, 1, 256, device=dev)
+    W2 = (0.02 * rn(H, 256, 64)).unsqueeze(0).repeat(B, 1, 1, 1).to(dev)
+    b2 = torch.zeros(B, H, 1, 64, device=dev)
+    params = [ln_w, ln_b, W1, b1, W2, b2]
+    if mode == "fwdbwd":
+        params = [p.requires_grad_(True) for p in params]
+
+    dq, dk, dv, de, dgo = (t.to(dev) for t in (XQ, XK, XV, eta_last, dOut))
+    launches = {"n": 0}
+    kern_ms = []
+
+    def step(q, k, v, e, go, time_kernels=False):
+        """One pass of the hot path through the public op (TkMLP.apply-compatible entry, last-row eta form)."""
+        if mode == "fwdbwd":
+            q = q.detach().requires_grad_(True); k = k.detach().requires_grad_(True); v = v.detach().requires_grad_(True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if time_kernels else None
+        if ev:
+            ev[0].record()
+        out = mlp_tk.ttt_mlp_op(*params, q, v, k, e, G)
+        if mode == "fwdbwd":
+            out.backward(go)
+        if ev:
+            ev[1].record()
+            kern_ms.append(ev)
+        launches["n"] += mlp_tk.launches_per_call(mode)
+        return out
+
+    for _ in range(args.warmup):
+        step(dq, dk, dv, de, dgo)
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches["n"] = 0
+    e0.record()
+    for _ in range(args.steps):
+        step(dq, dk, dv, de, dgo, time_kernels=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kern_ms) / max(1, len(kern_ms))
+    n_launch = launches["n"]
+
+    # ---- timed region 2: end to end from pinned host memory (H2D of this step's inputs, D2H of its result)
+    host_out = torch.empty(B, H, NC, 64, 64, dtype=torch.bfloat16).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (XQ, XK, XV, eta_last)) + (dOut.numel() * 2 if mode == "fwdbwd" else 0)
+    d2h = host_out.numel() * 2
+    for _ in range(2):
+        o = step(XQ.to(dev, non_blocking=True), XK.to(dev, non_blocking=True), XV.to(dev, non_blocking=True),
+                 eta_last.to(dev, non_blocking=True), dOut.to(dev, non_blocking=True) if mode == "fwdbwd" else None)
+        host_out.copy_(o.detach(), non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        o = step(XQ.to(dev, non_blocking=True), XK.to(dev, non_blocking=True), XV.to(dev, non_blocking=True),
+                 eta_last.to(dev, non_blocking=True), dOut.to(dev, non_blocking=True) if mode == "fwdbwd" else None)
+        host_out.copy_(o.detach(), non_blocking=True)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms_total, ms_e2e, kernel_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, kernel_ms = [float(x) for x in t]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    tokens_per_step = B * L * world
+    ms_per_step = ms_total / args.steps
+    value = tokens_per_step / (ms_per_step * 1e-3)
+    e2e_val = tokens_per_step / (ms_e2e / args.steps * 1e-3)
+    flop_per_step = B * H * NC * U_FLOP * (FWD_U + (BWD_U if mode == "fwdbwd" else 0))
+    burst, sustained, src = peaks()
+    achieved = flop_per_step / (kernel_ms * 1e-3) / 1e12
+    line = {
+        "metric": f"video-tokens/sec TTT-MLP layer-direction ({'fwd+bwd' if mode == 'fwdbwd' else 'fwd'})",
+        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"CogVideoX-5B TTT-MLP op ({'3-sec' if NC == 282 else str(NC) + ' mini-batch'} segment): B={B}/GPU, "
+                               f"{H} heads x 64, mini-batch 64, NC={NC} (L={L} tokens), checkpoint group {G}, one layer-direction",
+                   "mode": mode, "parallelism": f"dp{world} replicas (no data-path collective)",
+                   "l2": "inputs (q,k,v = %.0f MB) larger than the 126 MB L2; no explicit flush" % (3 * B * H * NC * 8192 / 1e6)},
+        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": n_launch,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                     "traffic": None, "peak_source": src + ", burst figure (op timed alone)",
+                     "kernel_ms": kernel_ms, "algorithmic_flop_per_step": flop_per_step},
+    }
+    if not args.no_cpu_baseline:
+        v, dt, sample = cpu_eager_tokens_per_s(H, mode, sample_nc=3, reps=1)
+        line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
