@@ -17,6 +17,7 @@
  */
 #ifndef TTT_B200_H
 #define TTT_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -35,6 +36,25 @@ int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const v
                          float* W1_ckpt, float* b1_ckpt, float* W2_ckpt, float* b2_ckpt,
                          float* W1_last, float* b1_last, float* W2_last, float* b2_last,
                          void* Out, int B, int H, int NC, int checkpoint_group_size, void* stream);
+
+/* TTT-MLP backward.  Replaces test_time_training.ttt_backward (ttt-tk/test_time_training.cpp:47-91,
+ * ttt-tk/kernels/ttt_backward/ttt.cu:1451-1917).  Inputs: the forward's inputs, its fp32 checkpoints and the upstream
+ * gradient dOut (bf16, layout of Out).  The upstream gradient of the final state is zero at this boundary
+ * (mlp_tk.py:179-182).  Outputs (caller-allocated; need not be pre-zeroed):
+ *   d_ln_weight, d_ln_bias  f32 [B,H,64]   (the caller sums over B, mlp_tk.py:277-278)
+ *   dW1 f32 [B,H,64,256]  db1 f32 [B,H,256]  dW2 f32 [B,H,256,64]  db2 f32 [B,H,64]   (w.r.t. the initial state)
+ *   d_last_eta bf16 [B,H,NC,CS]   dXQ, dXK, dXV bf16 [B,H,NC,CS,64]
+ * workspace: device scratch of at least ttt_b200_mlp_backward_workspace_bytes(B,H,G) bytes; it replaces the 16
+ * re-materialisation buffers the reference's caller allocates (mlp_tk.py:192-210). */
+size_t ttt_b200_mlp_backward_workspace_bytes(int B, int H, int checkpoint_group_size);
+int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta,
+                          const float* ln_weight, const float* ln_bias,
+                          const float* W1_ckpt, const float* b1_ckpt, const float* W2_ckpt, const float* b2_ckpt,
+                          const void* dOut,
+                          float* d_ln_weight, float* d_ln_bias, float* dW1, float* db1, float* dW2, float* db2,
+                          void* d_last_eta, void* dXQ, void* dXK, void* dXV,
+                          void* workspace, size_t workspace_bytes,
+                          int B, int H, int NC, int checkpoint_group_size, void* stream);
 
 /* Debug/self-test: D[128][N] = A[128][K] . Bm[K][N] through one tcgen05 CTA (see csrc/umma_selftest.cu). */
 int ttt_b200_debug_umma(int mode, const void* A_bf16, const void* B_bf16, float* D, int N, int K, void* stream);

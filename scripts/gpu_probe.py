@@ -28,6 +28,19 @@ for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,2,4,2),(2,3,7,3),(1,4,33,16)]:
     print('fwd', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'per-step', per,
           'ck', [O.rel_err(a.cpu(), b) for a,b in zip(ck, rck)], 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
 """ % (ROOT, ROOT),
+    "bwd": """
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from test_gpu_mlp_backward import errors
+for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,1,2,2),(1,2,3,2),(2,2,7,3),(1,3,20,16)]:
+    d = O.make_inputs(B,H,NC,seed=40+NC)
+    try:
+        e = errors(d, G)
+        print('bwd', (B,H,NC,G), {k: float('%%.3g' %% v) for k,v in e.items()}, flush=True)
+    except Exception as ex:
+        print('bwd', (B,H,NC,G), 'EXC', repr(ex)[:500], flush=True); break
+""" % (ROOT, ROOT),
 }
 
 if __name__ == "__main__":

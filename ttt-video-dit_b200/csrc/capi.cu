@@ -41,6 +41,28 @@ int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const v
                   "ttt_b200_mlp_forward");
 }
 
+size_t ttt_b200_mlp_backward_workspace_bytes(int B, int H, int G) { return tb::mlp_backward_workspace_bytes(B, H, G); }
+
+int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_weight,
+                          const float* ln_bias, const float* W1_ckpt, const float* b1_ckpt, const float* W2_ckpt,
+                          const float* b2_ckpt, const void* dOut, float* d_ln_weight, float* d_ln_bias, float* dW1,
+                          float* db1, float* dW2, float* db2, void* d_last_eta, void* dXQ, void* dXK, void* dXV,
+                          void* workspace, size_t workspace_bytes, int B, int H, int NC, int checkpoint_group_size,
+                          void* stream) {
+  if (!XQ || !XK || !XV || !last_eta || !ln_weight || !ln_bias || !W1_ckpt || !b1_ckpt || !W2_ckpt || !b2_ckpt || !dOut ||
+      !d_ln_weight || !d_ln_bias || !dW1 || !db1 || !dW2 || !db2 || !d_last_eta || !dXQ || !dXK || !dXV || !workspace)
+    return fail(-1, "ttt_b200_mlp_backward: null pointer argument");
+  if (B <= 0 || H <= 0 || NC <= 0 || checkpoint_group_size <= 0)
+    return fail(-2, "ttt_b200_mlp_backward: B, H, NC and checkpoint_group_size must be positive");
+  if (workspace_bytes < tb::mlp_backward_workspace_bytes(B, H, checkpoint_group_size))
+    return fail(-4, "ttt_b200_mlp_backward: workspace too small (see ttt_b200_mlp_backward_workspace_bytes)");
+  return cuda_ret(tb::launch_mlp_backward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, W2_ckpt, b2_ckpt,
+                                          dOut, d_ln_weight, d_ln_bias, dW1, db1, dW2, db2, d_last_eta, dXQ, dXK, dXV,
+                                          workspace, workspace_bytes, B, H, NC, checkpoint_group_size,
+                                          (cudaStream_t)stream),
+                  "ttt_b200_mlp_backward");
+}
+
 int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N, int K, void* stream) {
   return cuda_ret(tb::launch_umma_selftest(mode, A, Bm, D, N, K, (cudaStream_t)stream), "ttt_b200_debug_umma");
 }

@@ -20,3 +20,16 @@ cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, c
 cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float* D, int N, int K, cudaStream_t stream);
 
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_mlp_trajectory(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                  const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
+                                  const float* b2c, int B, int H, int NC, int K, int k, int t0, int nsteps,
+                                  uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream);
+size_t mlp_backward_workspace_bytes(int B, int H, int G);
+cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
+                                const float* b2c, const void* dOut, float* dlnw, float* dlnb, float* dW1, float* db1,
+                                float* dW2, float* db2, void* dEta, void* dXQ, void* dXK, void* dXV, void* workspace,
+                                size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream);
+}  // namespace tb

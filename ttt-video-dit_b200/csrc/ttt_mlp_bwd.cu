@@ -1,0 +1,866 @@
+// TTT-MLP backward for sm_100a.  Replaces ttt-tk/kernels/ttt_backward/ttt.cu:179-1917 (bwd_ttt_mlp_ker / ttt_backward).
+//
+// Structure (differs from the reference on purpose, SURVEY 7 "Backward memory traffic"): per checkpoint group g, in
+// reverse order, two launches:
+//   1. trajectory  (ttt_mlp_fwd_kernel<true>, csrc/ttt_mlp_fwd.cu): re-runs the K side of the group's steps from the
+//      fp32 checkpoint and stores only the bf16 operand images of each state W_t (64 KB/step, L2 resident) -- the
+//      reference spills 16 intermediates per step (~338 KB/step);
+//   2. reverse     (this file): walks t = t_hi .. t_lo.  Iteration t uses ONE state image W_t for both the K side of
+//      step t (recompute + closed-form backward, SURVEY appendix B = ttt-tk/kernels/ttt_backward/matching.py:173-342)
+//      and the Q side of step t-1 (which only needs the state *after* step t-1, i.e. W_t).
+// dW1^T, dW2 (grad w.r.t. the carried state) are persistent fp32 TMEM accumulators; between launches they live in a
+// small fp32 scratch.  Same "hidden units on TMEM lanes" layout as the forward; all tiles use SW128 row tiles.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+#include "ttt_internal.h"
+
+namespace tb {
+namespace bwd {
+
+constexpr int CS = 64, F = 64, HID = 256, NT = 256;
+
+// ---- shared memory map (bytes); total = 232448 = the 227 KB per-CTA maximum
+constexpr uint32_t SM_W2I = 0;         // W2 image of W_t                     [256][64] bf16
+constexpr uint32_t SM_HS = 32768;      // 4 hidden-lane tile slots of 32 KB (roles rotate, see kernel)
+constexpr uint32_t SM_TK = 163840;     // K_t   [64][64]
+constexpr uint32_t SM_TQ = 172032;     // Q_{t-1}
+constexpr uint32_t SM_TV = 180224;     // V_t
+constexpr uint32_t SM_TDO = 188416;    // dOut_{t-1}
+constexpr uint32_t SM_TT0 = 196608;    // dZ2 (K side) / dZbar2 (Q side)
+constexpr uint32_t SM_TT1 = 204800;    // gradZ2
+constexpr uint32_t SM_TT2 = 212992;    // -eta*gradZ2
+constexpr uint32_t SM_MISC = 221184;   // small fp32 vectors, barriers
+constexpr uint32_t SM_TOTAL = SM_MISC + 4096;  // 225280
+
+// ---- TMEM columns
+constexpr uint32_t TM_DW1 = 0;    // dW1^T accumulator, + 64*h
+constexpr uint32_t TM_DW2 = 128;  // dW2   accumulator, + 64*h
+constexpr uint32_t TM_S0 = 256, TM_S1 = 320, TM_S2 = 384, TM_S3 = 448;  // working slots of 64 columns
+
+struct BwdParams {
+  const __nv_bfloat16* last_eta;  // [B,H,NC,64]
+  const float *ln_w, *ln_b;       // [H,64]
+  const uint8_t* img;             // [BH][img_slots] x 64 KB  {W1^T image, W2 image}
+  const float *b1img, *b2img;     // [BH][img_slots][256], [BH][img_slots][64]
+  float *dW1s, *dW2s, *db1s, *db2s;  // carried state gradient, fp32: [BH][256][64] x2, [BH][256], [BH][64]
+  uint8_t* x2spill;                  // [BH][32 KB]
+  __nv_bfloat16 *dXQ, *dXK, *dXV, *dEta;  // outputs
+  float *dlnw, *dlnb;                     // [BH][64], accumulated with atomics (pre-zeroed by the host wrapper)
+  float *dW1, *db1, *dW2, *db2;           // final gradient w.r.t. the initial state (written when t_lo == 0)
+  int H, NC, img_slots;
+  int t_hi, t_lo, t0;  // iterations t_hi..t_lo (descending); image slot of W_t is t - t0
+  int first;           // 1: start from zero state gradient, 0: load it from the scratch
+};
+
+__device__ __forceinline__ void gelu3(float z, float& g0, float& g1, float& g2) {
+  // gelu, gelu' (ops/utils.py:51-54) and gelu'' (ttt_backward/matching.py:47-55)
+  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
+  const float z2 = z * z;
+  const float a = fmaf(3.0f * c1, z2, c0);
+  const float t = tanh_fast(z * fmaf(c1, z2, c0));
+  const float s = fmaf(-t, t, 1.0f);
+  const float hz = 0.5f * z;
+  g0 = fmaf(hz, t, hz);
+  g1 = fmaf(hz * s, a, fmaf(0.5f, t, 0.5f));
+  g2 = s * (fmaf(2.0f, a, -c0) - z * t * a * a);
+}
+__device__ __forceinline__ float gelu1(float z, float& g1) {
+  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
+  const float z2 = z * z;
+  const float t = tanh_fast(z * fmaf(c1, z2, c0));
+  const float hz = 0.5f * z;
+  g1 = fmaf(hz * fmaf(-t, t, 1.0f), fmaf(3.0f * c1, z2, c0), fmaf(0.5f, t, 0.5f));
+  return fmaf(hz, t, hz);
+}
+
+// 32 fp32 -> bf16 -> 4 consecutive chunks of one SW128 row
+__device__ __forceinline__ void st_row32(uint32_t tile, int row, int chunk0, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    st_shared_v4(tile + sw128_off(row, chunk0 + c), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+// read one 64-wide bf16 row of a SW128 tile into fp32
+__device__ __forceinline__ void ld_row64(uint32_t tile, int row, float* v) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t a, b, cc, d;
+    ld_shared_v4(tile + sw128_off(row, c), a, b, cc, d);
+    v[8 * c + 0] = bf16_lo(a); v[8 * c + 1] = bf16_hi(a); v[8 * c + 2] = bf16_lo(b); v[8 * c + 3] = bf16_hi(b);
+    v[8 * c + 4] = bf16_lo(cc); v[8 * c + 5] = bf16_hi(cc); v[8 * c + 6] = bf16_lo(d); v[8 * c + 7] = bf16_hi(d);
+  }
+}
+// column sums over the 32 lanes of a warp of a per-lane vector v[N] (N = 32 or 64) by recursive halving.
+// On return lane l holds in v[0] the sum of element l (N=32) or in v[0], v[1] the sums of elements l and l+32 (N=64).
+template <int N>
+__device__ __forceinline__ void warp_colsum(float* v, int lane) {
+  if (N == 64) {  // first fold 64 -> 32 pairs kept as (v[q], v[q+32]) handled by two independent 32-wide reductions
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int q = 0; q < m; ++q) {
+        float a0 = v[q], b0 = v[q + m], a1 = v[32 + q], b1 = v[32 + q + m];
+        float s0 = up ? a0 : b0, k0 = up ? b0 : a0, s1 = up ? a1 : b1, k1 = up ? b1 : a1;
+        v[q] = k0 + __shfl_xor_sync(0xffffffffu, s0, m);
+        v[32 + q] = k1 + __shfl_xor_sync(0xffffffffu, s1, m);
+      }
+    }
+    v[1] = v[32];
+  } else {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int q = 0; q < m; ++q) {
+        float a0 = v[q], b0 = v[q + m];
+        float s0 = up ? a0 : b0, k0 = up ? b0 : a0;
+        v[q] = k0 + __shfl_xor_sync(0xffffffffu, s0, m);
+      }
+    }
+  }
+}
+
+// ---- MMA issue helpers (single thread) -----------------------------------------------------------------------------
+// hidden-lane output: D[h] (128 lanes x N cols) = A_tile[h] (K-major, [256][64]) . B  ; 4 k-steps
+__device__ __forceinline__ void mma_hid(uint32_t d0, uint32_t d1, uint32_t a_tile, uint32_t b_tile, bool b_mn, int n,
+                                        bool acc) {
+  const uint32_t idesc = make_idesc_bf16(128, n, false, b_mn);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint64_t da = make_desc_sw128(a_tile + h * 16384, 16, 1024);
+    const uint64_t db = b_mn ? make_desc_sw128(b_tile, 1024, 1024) : make_desc_sw128(b_tile, 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_ss(h ? d1 : d0, desc_advance(da, 32 * k), desc_advance(db, b_mn ? 2048 * k : 32 * k), idesc, acc || k > 0);
+  }
+}
+// token-lane output: D (rows 0-63 valid) = A_tile (hidden-lane tile viewed MN-major, [256 j][64 tok]) . B_tile ([256 j][64 f],
+// MN-major); 16 k-steps over the hidden dim.  Rows 64-127 of D come from whatever lies 32 KB after A_tile (never read).
+__device__ __forceinline__ void mma_tok(uint32_t d, uint32_t a_tile, uint32_t b_tile, bool acc) {
+  const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+  const uint64_t da = make_desc_sw128(a_tile, 32768, 1024);
+  const uint64_t db = make_desc_sw128(b_tile, 1024, 1024);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) umma_ss(d, desc_advance(da, 2048 * k), desc_advance(db, 2048 * k), idesc, acc || k > 0);
+}
+
+#define MMA_WAIT()                 \
+  do {                             \
+    mbar_wait(mma_bar, mma_phase); \
+    mma_phase ^= 1;                \
+    tc_fence_after();              \
+  } while (0)
+#define PHASE_SYNC()     \
+  do {                   \
+    fence_proxy_async(); \
+    tc_fence_before();   \
+    __syncthreads();     \
+  } while (0)
+
+__global__ void __launch_bounds__(NT, 1)
+ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x, head = bh % p.H;
+  const int half = warp >> 2;
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+  const int j = tid;
+
+  float* lnw = reinterpret_cast<float*>(smem + SM_MISC);  // [64]
+  float* lnb = lnw + 64;
+  float* b2t = lnb + 64;      // b2 of W_t
+  float* db2c = b2t + 64;     // d b2 carried (grad w.r.t. b2 after step t; updated in place during the iteration)
+  float* etas = db2c + 64;    // eta of step t
+  float* etapart = etas + 64;  // [8 warps][64]: per-warp partial sums over hidden units for d eta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC + 3584);
+  uint64_t* mma_bar = bars;       // tcgen05.commit
+  uint64_t* bar_kv = bars + 1;    // K_t, V_t tiles
+  uint64_t* bar_qd = bars + 2;    // Q_{t-1}, dO_{t-1} tiles
+  uint64_t* bar_w1 = bars + 3;    // W1 image at iteration start
+  uint64_t* bar_w1r = bars + 4;   // W1 image reload (for dK / dQ GEMMs)
+  uint64_t* bar_w2 = bars + 5;    // W2 image
+  uint64_t* bar_x2 = bars + 6;    // X2 tile reload
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  if (tid < 64) {
+    lnw[tid] = p.ln_w[head * 64 + tid];
+    lnb[tid] = p.ln_b[head * 64 + tid];
+    db2c[tid] = p.first ? 0.f : p.db2s[(size_t)bh * 64 + tid];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  // ---- carried state gradient -> TMEM
+  float db1r = p.first ? 0.f : p.db1s[(size_t)bh * HID + j];
+  {
+    uint32_t v[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = p.first ? 0u : __float_as_uint(p.dW1s[((size_t)bh * HID + j) * F + 32 * c + i]);
+      tmem_st32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = p.first ? 0u : __float_as_uint(p.dW2s[((size_t)bh * HID + j) * F + 32 * c + i]);
+      tmem_st32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, v);
+    }
+    tc_wait_st();
+  }
+  const uint8_t* img_bh = p.img + (size_t)bh * p.img_slots * 65536;
+  const size_t row_bh = (size_t)bh * p.NC * CS;  // token row of step 0 of this sequence
+
+  // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
+  uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
+  uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0;
+  float dg_lo = 0.f, dg_hi = 0.f, dbt_lo = 0.f, dbt_hi = 0.f;  // d gamma / d beta partial sums of this lane (f = lane, lane+32)
+
+  // first iteration's loads
+  if (tid == 0) {
+    const int t = p.t_hi;
+    const uint8_t* im = img_bh + (size_t)(t - p.t0) * 65536;
+    mbar_expect_tx(bar_w1, 32768);
+    bulk_load_1d(smem + sW1, im, 32768, bar_w1);
+    mbar_expect_tx(bar_w2, 32768);
+    bulk_load_1d(smem + SM_W2I, im + 32768, 32768, bar_w2);
+    if (t < p.NC) {
+      mbar_expect_tx(bar_kv, 16384);
+      tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
+      tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
+    }
+    if (t > 0) {
+      mbar_expect_tx(bar_qd, 16384);
+      tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)(t - 1) * CS), bar_qd);
+      tma_load_2d(smem + SM_TDO, &tmDO, 0, (int)(row_bh + (size_t)(t - 1) * CS), bar_qd);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
+
+  for (int t = p.t_hi; t >= p.t_lo; --t) {
+    const bool has_k = t < p.NC, has_q = t > 0;
+    const size_t slot = (size_t)(t - p.t0);
+    const float b1t = p.b1img[((size_t)bh * p.img_slots + slot) * HID + j];
+    if (tid < 64) {
+      b2t[tid] = p.b2img[((size_t)bh * p.img_slots + slot) * F + tid];
+      if (has_k) etas[tid] = __bfloat162float(p.last_eta[row_bh + (size_t)t * CS + tid]);
+    }
+    mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1;
+    mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1;
+    if (has_k) { mbar_wait(bar_kv, ph_kv); ph_kv ^= 1; }
+    if (has_q) { mbar_wait(bar_qd, ph_qd); ph_qd ^= 1; }
+    __syncthreads();  // b2t / etas visible
+
+    if (has_k) {
+      // ===== A0 [H]: bf16 copies of the carried gradient accumulators: CW1 -> sA, CW2 -> sB
+      {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+          st_row32(sbase + sA, j, 4 * c, v);
+          tmem_ld32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+          st_row32(sbase + sB, j, 4 * c, v);
+        }
+      }
+      PHASE_SYNC();
+      // ===== A1 MMA: R1 = W1 . K^T -> (S0,S1)
+      if (tid == 0) {
+        tc_fence_after();
+        mma_hid(tmem + TM_S0, tmem + TM_S1, sbase + sW1, sbase + SM_TK, false, 64, false);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // ===== A2 [H]: Z1 -> X2 tile (sC), gelu', gelu''
+      {
+        const uint32_t src = tmem + lane_addr + (half ? TM_S1 : TM_S0);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0, x1, a0, a1, c0, c1;
+            gelu3(v[i] + b1t, x0, a0, c0);
+            gelu3(v[i + 1] + b1t, x1, a1, c1);
+            v[i] = x0; v[i + 1] = x1;
+            g1p[16 * c + i / 2] = pack_bf16(a0, a1);
+            g2p[16 * c + i / 2] = pack_bf16(c0, c1);
+          }
+          st_row32(sbase + sC, j, 4 * c, v);
+        }
+      }
+      PHASE_SYNC();
+      // ===== A3 MMA: R2: Z2 = X2 . W2 -> S2 ; B5: acc5 = X2 . CW2 -> S3
+      if (tid == 0) {
+        tc_fence_after();
+        mma_tok(tmem + TM_S2, sbase + sC, sbase + SM_W2I, false);
+        mma_tok(tmem + TM_S3, sbase + sC, sbase + sB, false);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // spill the X2 tile to L2 (needed again by the dW2 += X2^T dZ2 GEMM at the end of the K side)
+      if (tid == 0) {
+        bulk_store_1d(p.x2spill + (size_t)bh * 32768, smem + sC, 32768);
+        bulk_commit();
+      }
+      // ===== A4 [T]: LN forward stats, gradZ2 -> TT1, -eta*gradZ2 -> TT2, dg2p = -eta(acc5+db2') -> S3, d eta partial
+      float e_acc = 0.f;
+      if (warp < 2) {
+        const int r = tid;
+        float z[64], tg[64];
+        {
+          float kk[64];
+          ld_row64(sbase + SM_TK, r, kk);
+          ld_row64(sbase + SM_TV, r, tg);
+#pragma unroll
+          for (int f = 0; f < 64; ++f) tg[f] -= kk[f];
+        }
+        tmem_ld32(tmem + lane_addr + TM_S2, reinterpret_cast<uint32_t*>(z));
+        tmem_ld32(tmem + lane_addr + TM_S2 + 32, reinterpret_cast<uint32_t*>(z + 32));
+        tc_wait_ld();
+        float mu = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) { z[f] += b2t[f]; mu += z[f]; }
+        mu *= (1.f / 64.f);
+        float var = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
+        const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) {
+          z[f] *= rstd;                                          // x_hat
+          tg[f] = (fmaf(lnw[f], z[f], lnb[f]) - tg[f]) * lnw[f];  // gxh
+          s1 += tg[f];
+          s2 = fmaf(tg[f], z[f], s2);
+        }
+        const float eta = etas[r];
+#pragma unroll
+        for (int f = 0; f < 64; ++f) z[f] = (fmaf(64.f, tg[f], -s1) - z[f] * s2) * (rstd * (1.f / 64.f));  // gradZ2
+        st_row32(sbase + SM_TT1, r, 0, z);
+        st_row32(sbase + SM_TT1, r, 4, z + 32);
+#pragma unroll
+        for (int f = 0; f < 64; ++f) tg[f] = -eta * z[f];
+        st_row32(sbase + SM_TT2, r, 0, tg);
+        st_row32(sbase + SM_TT2, r, 4, tg + 32);
+        // acc5 -> dg2p (in place in S3), d eta partial
+        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(tg));
+        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(tg + 32));
+        tc_wait_ld();
+#pragma unroll
+        for (int f = 0; f < 64; ++f) {
+          const float a = tg[f] + db2c[f];
+          e_acc = fmaf(-z[f], a, e_acc);
+          tg[f] = -eta * a;
+        }
+        tmem_st32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(tg));
+        tmem_st32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(tg + 32));
+        tc_wait_st();
+      }
+      if (tid == 0) bulk_wait_read<0>();  // X2 tile has been read out of smem: slot sC may be overwritten
+      PHASE_SYNC();
+
+      // ===== A5/A6 (two chunks of 32 tokens): pre = W2 . gradZ2^T -> S0, raw = CW1 . K^T -> S1 (N = 32);
+      //       [H]: gradZ1, d gradZ1, DG1 -> sW1, G1eta -> sC, term2, d eta hidden-sums
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (tid == 0) {
+          tc_fence_after();
+          mma_hid(tmem + TM_S0, tmem + TM_S0 + 32, sbase + SM_W2I, sbase + SM_TT1 + ch * 4096, false, 32, false);
+          mma_hid(tmem + TM_S1, tmem + TM_S1 + 32, sbase + sA, sbase + SM_TK + ch * 4096, false, 32, false);
+          tc_commit(mma_bar);
+        }
+        MMA_WAIT();
+        {
+          float pre[32], raw[32];
+          tmem_ld32(tmem + lane_addr + TM_S0 + 32 * half, reinterpret_cast<uint32_t*>(pre));
+          tmem_ld32(tmem + lane_addr + TM_S1 + 32 * half, reinterpret_cast<uint32_t*>(raw));
+          tc_wait_ld();
+          float ep[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t gp1 = g1p[16 * ch + i / 2], gp2 = g2p[16 * ch + i / 2];
+            const float et0 = etas[32 * ch + i], et1 = etas[32 * ch + i + 1];
+            const float gz0 = pre[i] * bf16_lo(gp1), gz1 = pre[i + 1] * bf16_hi(gp1);   // gradZ1
+            const float E0 = raw[i] + db1r, E1 = raw[i + 1] + db1r;
+            const float d0 = -et0 * E0, d1 = -et1 * E1;                                 // d gradZ1
+            ep[i] = gz0 * E0; ep[i + 1] = gz1 * E1;
+            g2p[16 * ch + i / 2] = pack_bf16(pre[i] * d0 * bf16_lo(gp2), pre[i + 1] * d1 * bf16_hi(gp2));  // term2
+            raw[i] = d0 * bf16_lo(gp1); raw[i + 1] = d1 * bf16_hi(gp1);                 // DG1
+            pre[i] = -et0 * gz0; pre[i + 1] = -et1 * gz1;                               // G1eta
+          }
+          st_row32(sbase + sW1, j, 4 * ch, raw);
+          st_row32(sbase + sC, j, 4 * ch, pre);
+          warp_colsum<32>(ep, lane);
+          etapart[warp * 64 + 32 * ch + lane] = ep[0];
+        }
+        PHASE_SYNC();
+      }
+      // ===== A7 MMA: dK acc: S0 = G1eta . CW1 ; S3 += DG1 . W2
+      if (tid == 0) {
+        tc_fence_after();
+        mma_tok(tmem + TM_S0, sbase + sC, sbase + sA, false);
+        mma_tok(tmem + TM_S3, sbase + sW1, sbase + SM_W2I, true);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      if (tid == 0) {  // sA (CW1) and sC (G1eta) are free: reload the W1 image and the X2 tile
+        bulk_wait<0>();
+        mbar_expect_tx(bar_w1r, 32768);
+        bulk_load_1d(smem + sA, img_bh + slot * 65536, 32768, bar_w1r);
+        mbar_expect_tx(bar_x2, 32768);
+        bulk_load_1d(smem + sC, p.x2spill + (size_t)bh * 32768, 32768, bar_x2);
+      }
+      // ===== A8 [T]: stage 2 (backward through the fused LN + L2 gradient), dZ2 -> TT0, dV, d eta, fold -dtarget into S0
+      if (warp < 2) {
+        const int r = tid;
+        float z[64], dg[64], o[64];
+        tmem_ld32(tmem + lane_addr + TM_S2, reinterpret_cast<uint32_t*>(z));
+        tmem_ld32(tmem + lane_addr + TM_S2 + 32, reinterpret_cast<uint32_t*>(z + 32));
+        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(dg));
+        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(dg + 32));
+        tc_wait_ld();
+        float mu = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) { z[f] += b2t[f]; mu += z[f]; }
+        mu *= (1.f / 64.f);
+        float var = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
+        const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
+        float s1 = 0.f, s2 = 0.f, sd = 0.f, sdx = 0.f;
+        // pass 1: x_hat, go = gamma*xhat + beta - (V-K) kept in o[], row sums
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t kk[4], vv[4];
+          ld_shared_v4(sbase + SM_TK + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
+          ld_shared_v4(sbase + SM_TV + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = 8 * c + e;
+            const float tgt = (e & 1) ? (bf16_hi(vv[e >> 1]) - bf16_hi(kk[e >> 1])) : (bf16_lo(vv[e >> 1]) - bf16_lo(kk[e >> 1]));
+            z[f] *= rstd;
+            o[f] = fmaf(lnw[f], z[f], lnb[f]) - tgt;  // go
+            const float gxh = o[f] * lnw[f];
+            s1 += gxh;
+            s2 = fmaf(gxh, z[f], s2);
+            sd += dg[f];
+            sdx = fmaf(dg[f], z[f], sdx);
+          }
+        }
+        // pass 2: d gamma contribution -> colsum ; sums of d_sigma and d_xhat
+        float sds = 0.f, sdxh = 0.f;
+        {
+          float cg[64];
+#pragma unroll
+          for (int f = 0; f < 64; ++f) {
+            const float gxh = o[f] * lnw[f];
+            const float gz2 = (fmaf(64.f, gxh, -s1) - z[f] * s2) * (rstd * (1.f / 64.f));
+            const float dgxh = rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
+            const float dy = lnw[f] * dgxh;
+            cg[f] = fmaf(o[f], dgxh, dy * z[f]);
+            const float dxh = fmaf(dy, lnw[f], -(rstd * (1.f / 64.f)) * fmaf(gxh, sdx, dg[f] * s2));
+            sds += (-dxh * z[f] - dg[f] * gz2) * rstd;
+            sdxh += dxh;
+          }
+          warp_colsum<64>(cg, lane);
+          dg_lo += cg[0]; dg_hi += cg[1];
+        }
+        // pass 3: dy -> dV (global), fold +dy into the dK accumulator S0, d beta colsum
+        {
+          float dy[64];
+#pragma unroll
+          for (int f = 0; f < 64; ++f) dy[f] = lnw[f] * rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
+          __nv_bfloat16* gv = p.dXV + (row_bh + (size_t)t * CS + r) * F;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(gv + 8 * c) =
+                make_uint4(pack_bf16(-dy[8 * c], -dy[8 * c + 1]), pack_bf16(-dy[8 * c + 2], -dy[8 * c + 3]),
+                           pack_bf16(-dy[8 * c + 4], -dy[8 * c + 5]), pack_bf16(-dy[8 * c + 6], -dy[8 * c + 7]));
+          float a[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tmem + lane_addr + TM_S0 + 32 * c, reinterpret_cast<uint32_t*>(a));
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] += dy[32 * c + i];
+            tmem_st32(tmem + lane_addr + TM_S0 + 32 * c, reinterpret_cast<uint32_t*>(a));
+          }
+          tc_wait_st();
+          warp_colsum<64>(dy, lane);
+          dbt_lo += dy[0]; dbt_hi += dy[1];
+        }
+        // pass 4: dZ2 -> TT0 tile, d b2 colsum
+#pragma unroll
+        for (int f = 0; f < 64; ++f) {
+          const float gxh = o[f] * lnw[f];
+          const float dy = lnw[f] * rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
+          const float dxh = fmaf(dy, lnw[f], -(rstd * (1.f / 64.f)) * fmaf(gxh, sdx, dg[f] * s2));
+          o[f] = fmaf(dxh, rstd, (1.f / 64.f) * (z[f] * sds - sdxh * rstd));
+        }
+        st_row32(sbase + SM_TT0, r, 0, o);
+        st_row32(sbase + SM_TT0, r, 4, o + 32);
+        warp_colsum<64>(o, lane);
+        atomicAdd(&db2c[lane], o[0]);
+        atomicAdd(&db2c[lane + 32], o[1]);
+        {  // d eta of step t
+          float e = e_acc;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) e -= etapart[w * 64 + r];
+          p.dEta[row_bh + (size_t)t * CS + r] = __float2bfloat16(e);
+        }
+      }
+      PHASE_SYNC();
+      // ===== A9 MMA: dX2^T = W2 . dZ2^T + CW2 . (-eta gradZ2)^T -> (S1,S2)
+      if (tid == 0) {
+        tc_fence_after();
+        mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + SM_W2I, sbase + SM_TT0, false, 64, false);
+        mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + sB, sbase + SM_TT2, false, 64, true);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // ===== A10 [H]: dZ1 = dX2 * gelu'(Z1) + term2 -> sB ; d b1 += sum dZ1
+      {
+        const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t gp1 = g1p[16 * c + i / 2], tp = g2p[16 * c + i / 2];
+            v[i] = fmaf(v[i], bf16_lo(gp1), bf16_lo(tp));
+            v[i + 1] = fmaf(v[i + 1], bf16_hi(gp1), bf16_hi(tp));
+            acc += v[i] + v[i + 1];
+          }
+          st_row32(sbase + sB, j, 4 * c, v);
+        }
+        db1r += acc;
+      }
+      mbar_wait(bar_w1r, ph_w1r); ph_w1r ^= 1;
+      mbar_wait(bar_x2, ph_x2); ph_x2 ^= 1;
+      PHASE_SYNC();
+      // ===== A11 MMA: dK: S0 += dZ1 . W1 ; dW2 += DG1^T gradZ2 + X2^T dZ2 ; dW1^T += dZ1^T K
+      if (tid == 0) {
+        tc_fence_after();
+        mma_tok(tmem + TM_S0, sbase + sB, sbase + sA, true);
+        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sW1, sbase + SM_TT1, true, 64, true);
+        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sC, sbase + SM_TT0, true, 64, true);
+        mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TK, true, 64, true);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // ===== A12 [T]: dK -> global
+      if (warp < 2) {
+        const int r = tid;
+        float a[64];
+        tmem_ld32(tmem + lane_addr + TM_S0, reinterpret_cast<uint32_t*>(a));
+        tmem_ld32(tmem + lane_addr + TM_S0 + 32, reinterpret_cast<uint32_t*>(a + 32));
+        tc_wait_ld();
+        __nv_bfloat16* gk = p.dXK + (row_bh + (size_t)t * CS + r) * F;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(gk + 8 * c) =
+              make_uint4(pack_bf16(a[8 * c], a[8 * c + 1]), pack_bf16(a[8 * c + 2], a[8 * c + 3]),
+                         pack_bf16(a[8 * c + 4], a[8 * c + 5]), pack_bf16(a[8 * c + 6], a[8 * c + 7]));
+      }
+      tc_fence_before();
+      __syncthreads();
+    } else {
+      // Q-only iteration (t == NC): the W1 image sits in sW1; the Q chain below expects it in sA
+      const uint32_t tmp = sA; sA = sW1; sW1 = tmp;
+    }
+
+    // next iteration's K/V tiles and W1 image (their buffers are free now)
+    const bool more = t > p.t_lo;
+    if (tid == 0 && more) {
+      const int tn = t - 1;  // always < NC
+      mbar_expect_tx(bar_kv, 16384);
+      tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);
+      tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);
+      mbar_expect_tx(bar_w1, 32768);
+      bulk_load_1d(smem + sC, img_bh + (size_t)(tn - p.t0) * 65536, 32768, bar_w1);
+    }
+
+    if (has_q) {
+      // ===== Q1 MMA: Zbar1^T = W1 . Q^T -> (S1,S2)
+      if (tid == 0) {
+        tc_fence_after();
+        mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + sA, sbase + SM_TQ, false, 64, false);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // ===== Q2 [H]: X2bar -> sB, gelu'(Zbar1)
+      {
+        const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            v[i] = gelu1(v[i] + b1t, a0);
+            v[i + 1] = gelu1(v[i + 1] + b1t, a1);
+            g1p[16 * c + i / 2] = pack_bf16(a0, a1);
+          }
+          st_row32(sbase + sB, j, 4 * c, v);
+        }
+      }
+      PHASE_SYNC();
+      // ===== Q3 MMA: Zbar2 = X2bar . W2 -> S3
+      if (tid == 0) {
+        tc_fence_after();
+        mma_tok(tmem + TM_S3, sbase + sB, sbase + SM_W2I, false);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // ===== Q4 [T]: output LN backward: dZbar2 -> TT0 ; d gamma, d beta, d b2
+      if (warp < 2) {
+        const int r = tid;
+        float z[64], d[64];
+        ld_row64(sbase + SM_TDO, r, d);
+        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(z));
+        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(z + 32));
+        tc_wait_ld();
+        float mu = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) { z[f] += b2t[f]; mu += z[f]; }
+        mu *= (1.f / 64.f);
+        float var = 0.f;
+#pragma unroll
+        for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
+        const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
+        float s1 = 0.f, s2 = 0.f;
+        float cg[64];
+#pragma unroll
+        for (int f = 0; f < 64; ++f) {
+          z[f] *= rstd;
+          cg[f] = d[f] * z[f];               // d gamma contribution
+          const float dxh = d[f] * lnw[f];
+          s1 += dxh;
+          s2 = fmaf(dxh, z[f], s2);
+        }
+#pragma unroll
+        for (int f = 0; f < 64; ++f)
+          z[f] = (fmaf(64.f, d[f] * lnw[f], -s1) - z[f] * s2) * (rstd * (1.f / 64.f));  // dZbar2
+        st_row32(sbase + SM_TT0, r, 0, z);
+        st_row32(sbase + SM_TT0, r, 4, z + 32);
+        warp_colsum<64>(z, lane);
+        atomicAdd(&db2c[lane], z[0]);
+        atomicAdd(&db2c[lane + 32], z[1]);
+        warp_colsum<64>(cg, lane);
+        dg_lo += cg[0]; dg_hi += cg[1];
+        warp_colsum<64>(d, lane);
+        dbt_lo += d[0]; dbt_hi += d[1];
+      }
+      PHASE_SYNC();
+      // ===== Q5 MMA: dX2bar^T = W2 . dZbar2^T -> (S1,S2) ; dW2 += X2bar^T dZbar2
+      if (tid == 0) {
+        tc_fence_after();
+        mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + SM_W2I, sbase + SM_TT0, false, 64, false);
+        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sB, sbase + SM_TT0, true, 64, true);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      if (tid == 0 && more) {  // W2 image buffer is free: fetch the next one
+        mbar_expect_tx(bar_w2, 32768);
+        bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
+      }
+      // ===== Q6 [H]: dZbar1 = dX2bar * gelu'(Zbar1) -> sW1 ; d b1 += sum
+      {
+        const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t gp1 = g1p[16 * c + i / 2];
+            v[i] *= bf16_lo(gp1);
+            v[i + 1] *= bf16_hi(gp1);
+            acc += v[i] + v[i + 1];
+          }
+          st_row32(sbase + sW1, j, 4 * c, v);
+        }
+        db1r += acc;
+      }
+      PHASE_SYNC();
+      // ===== Q7 MMA: dW1^T += dZbar1^T Q ; dQ_u = dZbar1 . W1 -> S3
+      if (tid == 0) {
+        tc_fence_after();
+        mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sW1, sbase + SM_TQ, true, 64, true);
+        mma_tok(tmem + TM_S3, sbase + sW1, sbase + sA, false);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+      // ===== Q8 [T]: dQ = dO + dQ_u
+      if (warp < 2) {
+        const int r = tid;
+        float a[64], d[64];
+        ld_row64(sbase + SM_TDO, r, d);
+        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(a));
+        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(a + 32));
+        tc_wait_ld();
+        __nv_bfloat16* gq = p.dXQ + (row_bh + (size_t)(t - 1) * CS + r) * F;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(gq + 8 * c) = make_uint4(
+              pack_bf16(a[8 * c] + d[8 * c], a[8 * c + 1] + d[8 * c + 1]), pack_bf16(a[8 * c + 2] + d[8 * c + 2], a[8 * c + 3] + d[8 * c + 3]),
+              pack_bf16(a[8 * c + 4] + d[8 * c + 4], a[8 * c + 5] + d[8 * c + 5]), pack_bf16(a[8 * c + 6] + d[8 * c + 6], a[8 * c + 7] + d[8 * c + 7]));
+      }
+      tc_fence_before();
+      __syncthreads();
+    } else if (tid == 0 && more) {  // (cannot happen: t == 0 is always the last iteration) keep the W2 prefetch paired
+      mbar_expect_tx(bar_w2, 32768);
+      bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
+    }
+    // next iteration's Q / dO tiles
+    if (tid == 0 && more && (t - 1) > 0) {
+      mbar_expect_tx(bar_qd, 16384);
+      tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)(t - 2) * CS), bar_qd);
+      tma_load_2d(smem + SM_TDO, &tmDO, 0, (int)(row_bh + (size_t)(t - 2) * CS), bar_qd);
+    }
+    // rotate slot roles: the next W1 image was fetched into sC
+    {
+      const uint32_t n0 = sC, n1 = sW1, n2 = sA, n3 = sB;
+      sW1 = n0; sA = n1; sB = n2; sC = n3;
+    }
+  }
+
+  // ---- epilogue: carried gradient -> scratch (or final outputs), LN parameter gradients
+  tc_fence_after();
+  {
+    const bool fin = (p.t_lo == 0);
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
+      tc_wait_ld();
+      if (fin) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p.dW1[((size_t)bh * F + 32 * c + i) * HID + j] = v[i];  // [f][j] layout
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p.dW1s[((size_t)bh * HID + j) * F + 32 * c + i] = v[i];
+      }
+      tmem_ld32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
+      tc_wait_ld();
+      float* dst = (fin ? p.dW2 : p.dW2s) + ((size_t)bh * HID + j) * F + 32 * c;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[i] = v[i];
+    }
+    (fin ? p.db1 : p.db1s)[(size_t)bh * HID + j] = db1r;
+    if (tid < 64) (fin ? p.db2 : p.db2s)[(size_t)bh * 64 + tid] = db2c[tid];
+    if (warp < 2) {
+      atomicAdd(&p.dlnw[(size_t)bh * 64 + lane], dg_lo);
+      atomicAdd(&p.dlnw[(size_t)bh * 64 + lane + 32], dg_hi);
+      atomicAdd(&p.dlnb[(size_t)bh * 64 + lane], dbt_lo);
+      atomicAdd(&p.dlnb[(size_t)bh * 64 + lane + 32], dbt_hi);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace bwd
+
+// ------------------------------------------------------------------------------------------------ host
+size_t mlp_backward_workspace_bytes(int B, int H, int G) {
+  const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
+  return bh * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4 + 2 * 65536 + 1024 + 256 + 32768) + 1024;
+}
+
+cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
+                                const float* b2c, const void* dOut, float* dlnw, float* dlnb, float* dW1, float* db1,
+                                float* dW2, float* db2, void* dEta, void* dXQ, void* dXK, void* dXV, void* workspace,
+                                size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) return cudaErrorInvalidValue;
+  if (workspace_bytes < mlp_backward_workspace_bytes(B, H, G)) return cudaErrorInvalidValue;
+  const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  w = reinterpret_cast<uint8_t*>(((uintptr_t)w + 1023) & ~(uintptr_t)1023);
+  uint8_t* img = w;                      w += bh * slots * 65536;
+  uint8_t* x2s = w;                      w += bh * 32768;
+  float* dW1s = reinterpret_cast<float*>(w); w += bh * 65536;
+  float* dW2s = reinterpret_cast<float*>(w); w += bh * 65536;
+  float* b1img = reinterpret_cast<float*>(w); w += bh * slots * 1024;
+  float* b2img = reinterpret_cast<float*>(w); w += bh * slots * 256;
+  float* db1s = reinterpret_cast<float*>(w); w += bh * 1024;
+  float* db2s = reinterpret_cast<float*>(w); w += bh * 256;
+
+  CUtensorMap tq, tk, tv, tdo;
+  const uint64_t rows = (uint64_t)bh * NC * 64;
+  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+  if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows) ||
+      make_token_tmap(&tdo, dOut, rows))
+    return cudaErrorInvalidValue;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(bwd::ttt_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaError_t e = cudaMemsetAsync(dlnw, 0, bh * 64 * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(dlnb, 0, bh * 64 * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+
+  const int K = (NC + G - 1) / G;
+  for (int g = K - 1; g >= 0; --g) {
+    const int t0 = g * G;
+    const int t1 = (t0 + G < NC) ? t0 + G : NC;
+    const bool last = (g == K - 1);
+    // trajectory: images of W_{t0} .. W_{t1-1} (and W_NC for the last group)
+    e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0,
+                              last ? (t1 - t0) : (t1 - t0 - 1), img, b1img, b2img, (int)slots, stream);
+    if (e != cudaSuccess) return e;
+    bwd::BwdParams p{};
+    p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
+    p.ln_w = ln_w; p.ln_b = ln_b;
+    p.img = img; p.b1img = b1img; p.b2img = b2img;
+    p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
+    p.x2spill = x2s;
+    p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
+    p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = reinterpret_cast<__nv_bfloat16*>(dEta);
+    p.dlnw = dlnw; p.dlnb = dlnb;
+    p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
+    p.H = H; p.NC = NC; p.img_slots = (int)slots;
+    p.t_hi = last ? NC : t1 - 1;
+    p.t_lo = t0; p.t0 = t0;
+    p.first = last ? 1 : 0;
+    bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, tdo, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace tb

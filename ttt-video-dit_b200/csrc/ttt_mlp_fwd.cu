@@ -72,6 +72,12 @@ struct FwdParams {
   float *W1o, *b1o, *W2o, *b2o;        // final state (may be null)
   __nv_bfloat16* Out;                  // [B,H,NC,64,64]
   int B, H, NC, ckpt_group, K;
+  // trajectory mode (backward pass, csrc/ttt_mlp_bwd.cu): run steps [t0, t0+nsteps) from the state stored at
+  // W1[(bh*init_stride + init_off)] and save, for s = 0..nsteps, the bf16 operand images of the state entering step
+  // t0+s: img[(bh*(G+1)+s)] = { W1^T image 32 KB, W2 image 32 KB } in smem-tile byte order, b1img, b2img (fp32).
+  int t0, nsteps, init_stride, init_off, img_slots;
+  uint8_t* img;
+  float *b1img, *b2img;
 };
 
 // store one thread's state rows (fp32, still in registers) to a [64][256] W1 image and a [256][64] W2 image
@@ -87,17 +93,21 @@ __device__ __forceinline__ void store_w2_row(float* W2g, int j, const uint32_t* 
                          __uint_as_float(v[4 * i + 3]));
 }
 // 32 fp32 (registers) -> bf16 -> 4 chunks of a SW128 row
-__device__ __forceinline__ void store_row_bf16(uint32_t tile_saddr, int row, int chunk0, const uint32_t* v) {
+__device__ __forceinline__ void store_row_bf16(uint32_t tile_saddr, int row, int chunk0, const uint32_t* v,
+                                               uint8_t* gmirror = nullptr) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t p0 = pack_bf16(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
     uint32_t p1 = pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
     uint32_t p2 = pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
     uint32_t p3 = pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
-    st_shared_v4(tile_saddr + sw128_off(row, chunk0 + c), p0, p1, p2, p3);
+    const uint32_t off = sw128_off(row, chunk0 + c);
+    st_shared_v4(tile_saddr + off, p0, p1, p2, p3);
+    if (gmirror) *reinterpret_cast<uint4*>(gmirror + off) = make_uint4(p0, p1, p2, p3);
   }
 }
 
+template <bool kTraj>
 __global__ void __launch_bounds__(NT, 1)
 ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -106,7 +116,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x;
   const int head = bh % p.H;
-  const int NC = p.NC;
+  const int NC = kTraj ? p.nsteps : p.NC;  // number of steps this launch runs
 
   float* b2s = reinterpret_cast<float*>(smem + SM_MISC);
   float* lnw = b2s + 64;
@@ -129,7 +139,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (tid < 64) {
     lnw[tid] = p.ln_w[head * 64 + tid];
     lnb[tid] = p.ln_b[head * 64 + tid];
-    b2s[tid] = p.b2[(size_t)bh * 64 + tid];
+    b2s[tid] = p.b2[((size_t)bh * p.init_stride + p.init_off) * 64 + tid];
   }
   tc_fence_before();
   __syncthreads();
@@ -138,36 +148,42 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int half = warp >> 2;                                    // which 128-row half of the hidden dim
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;  // this warp's TMEM lane quarter
   const int j = tid;                                             // hidden unit owned by this thread (P2/P6/P8)
-  const size_t row_base = (size_t)bh * NC * CS;                   // first token row of this sequence in [B*H*NC*CS, 64]
+  const size_t row_base = ((size_t)bh * p.NC + (kTraj ? p.t0 : 0)) * CS;  // first token row handled, in [B*H*NC*CS, 64]
+  const size_t st_idx = (size_t)bh * p.init_stride + p.init_off;            // which stored state to start from
+  uint8_t* img0 = kTraj ? p.img + (size_t)bh * p.img_slots * 65536 : nullptr;
 
   // prologue TMA: K_0, V_0 into slot 0
-  if (tid == 0) {
+  if (tid == 0 && NC > 0) {
     mbar_expect_tx(&tma_bar[0], 16384);
     tma_load_2d(smem + SM_KQ, &tmK, 0, (int)row_base, &tma_bar[0]);
     tma_load_2d(smem + SM_V, &tmV, 0, (int)row_base, &tma_bar[0]);
   }
 
   // ---- initial state: global fp32 -> TMEM accumulators + bf16 operand copies (+ checkpoint 0)
-  float b1r = p.b1[(size_t)bh * HID + j];
+  float b1r = p.b1[st_idx * HID + j];
   {
-    const float* W1g = p.W1 + (size_t)bh * F * HID;
-    const float* W2g = p.W2 + (size_t)bh * HID * F;
+    const float* W1g = p.W1 + st_idx * F * HID;
+    const float* W2g = p.W2 + st_idx * HID * F;
     uint32_t v[32];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(W1g[(size_t)(32 * c + i) * HID + j]);
       tmem_st32(tmem + lane_addr + TM_W1 + 64 * half + 32 * c, v);
-      store_row_bf16(sbase + SM_W1B, j, 4 * c, v);
-      if (p.W1c) store_w1_col(p.W1c + ((size_t)bh * p.K) * F * HID, j, v, 32 * c);
+      store_row_bf16(sbase + SM_W1B, j, 4 * c, v, img0);
+      if (!kTraj && p.W1c) store_w1_col(p.W1c + ((size_t)bh * p.K) * F * HID, j, v, 32 * c);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(W2g[(size_t)j * F + 32 * c + i]);
       tmem_st32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
-      store_row_bf16(sbase + SM_W2B, j, 4 * c, v);
-      if (p.W2c) store_w2_row(p.W2c + ((size_t)bh * p.K) * HID * F, j, v, 32 * c);
+      store_row_bf16(sbase + SM_W2B, j, 4 * c, v, img0 ? img0 + 32768 : nullptr);
+      if (!kTraj && p.W2c) store_w2_row(p.W2c + ((size_t)bh * p.K) * HID * F, j, v, 32 * c);
     }
-    if (p.b1c) p.b1c[((size_t)bh * p.K) * HID + j] = b1r;
-    if (p.b2c && tid < 64) p.b2c[((size_t)bh * p.K) * F + tid] = p.b2[(size_t)bh * 64 + tid];
+    if (!kTraj && p.b1c) p.b1c[((size_t)bh * p.K) * HID + j] = b1r;
+    if (!kTraj && p.b2c && tid < 64) p.b2c[((size_t)bh * p.K) * F + tid] = p.b2[st_idx * 64 + tid];
+    if (kTraj) {
+      p.b1img[((size_t)bh * p.img_slots) * HID + j] = b1r;
+      if (tid < 64) p.b2img[((size_t)bh * p.img_slots) * F + tid] = p.b2[st_idx * 64 + tid];
+    }
     tc_wait_st();
   }
   fence_proxy_async();
@@ -175,6 +191,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
 
   constexpr uint32_t IDESC_A = make_idesc_bf16(128, 128, false, false);  // D1: A K-major, B K-major
+  constexpr uint32_t IDESC_A64 = make_idesc_bf16(128, 64, false, false);  // trajectory mode: K side only
   constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true);     // D2: A MN-major, B MN-major
   constexpr uint32_t IDESC_C = make_idesc_bf16(128, 64, false, false);   // D3
   constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
@@ -182,26 +199,26 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t mma_phase = 0;
   uint32_t gp[32];  // gelu'(Z1) for this thread's hidden unit, 64 tokens, packed bf16x2
 
-  for (int it = 0; it <= NC; ++it) {
+  for (int it = 0; it < (kTraj ? NC : NC + 1); ++it) {
     const int slot = it & 1;
-    const bool has_k = it < NC, has_q = it > 0;
+    const bool has_k = it < NC, has_q = !kTraj && it > 0;
     const uint32_t kq = sbase + SM_KQ + slot * 16384;
     const uint32_t vt = sbase + SM_V + slot * 8192;
 
     // prefetch eta for the LN threads of the K side
     float eta_i = 0.f;
-    if (has_k && warp < 2) eta_i = __bfloat162float(p.last_eta[((size_t)bh * NC + it) * CS + tid]);
+    if (has_k && warp < 2) eta_i = __bfloat162float(p.last_eta[row_base + (size_t)it * CS + tid]);
 
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
-    if (tid == 0 && it < NC) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
+    if (tid == 0 && (kTraj ? (it + 1 < NC) : (it < NC))) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
       const int ns = slot ^ 1;
       const bool nk = (it + 1) < NC;
-      mbar_expect_tx(&tma_bar[ns], nk ? 24576 : 8192);
+      mbar_expect_tx(&tma_bar[ns], (nk ? 16384 : 0) + (kTraj ? 0 : 8192));
       if (nk) {
         tma_load_2d(smem + SM_KQ + ns * 16384, &tmK, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
         tma_load_2d(smem + SM_V + ns * 8192, &tmV, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
       }
-      tma_load_2d(smem + SM_KQ + ns * 16384 + 8192, &tmQ, 0, (int)(row_base + (size_t)it * CS), &tma_bar[ns]);
+      if (!kTraj) tma_load_2d(smem + SM_KQ + ns * 16384 + 8192, &tmQ, 0, (int)(row_base + (size_t)it * CS), &tma_bar[ns]);
     }
 
     // ---------------- P1: D1[h] = W1b^T[h] . [K | Q]^T   (M=128, N=128, K=64)
@@ -213,7 +230,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint64_t db = make_desc_sw128(kq, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), IDESC_A, k > 0);
+          umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), kTraj ? IDESC_A64 : IDESC_A, k > 0);
       }
       tc_commit(mma_bar);
     }
@@ -444,26 +461,31 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ---------------- P8: re-materialise bf16 operand copies of the new state (+ checkpoint / final state)
     {
       const int nstep = it + 1;  // state now equals the state entering mini-batch nstep
-      const bool ck = (p.W1c != nullptr) && (nstep < NC) && (nstep % p.ckpt_group == 0);
-      const bool fin = (p.W1o != nullptr) && (nstep == NC);
+      const bool ck = !kTraj && (p.W1c != nullptr) && (nstep < NC) && (nstep % p.ckpt_group == 0);
+      const bool fin = !kTraj && (p.W1o != nullptr) && (nstep == NC);
+      uint8_t* imgs = kTraj ? img0 + (size_t)nstep * 65536 : nullptr;
       const size_t kidx = ck ? ((size_t)bh * p.K + nstep / p.ckpt_group) : 0;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + TM_W1 + 64 * half + 32 * c, v);
         tc_wait_ld();
-        store_row_bf16(sbase + SM_W1B, j, 4 * c, v);
+        store_row_bf16(sbase + SM_W1B, j, 4 * c, v, imgs);
         if (ck) store_w1_col(p.W1c + kidx * F * HID, j, v, 32 * c);
         if (fin) store_w1_col(p.W1o + (size_t)bh * F * HID, j, v, 32 * c);
         tmem_ld32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
         tc_wait_ld();
-        store_row_bf16(sbase + SM_W2B, j, 4 * c, v);
+        store_row_bf16(sbase + SM_W2B, j, 4 * c, v, imgs ? imgs + 32768 : nullptr);
         if (ck) store_w2_row(p.W2c + kidx * HID * F, j, v, 32 * c);
         if (fin) store_w2_row(p.W2o + (size_t)bh * HID * F, j, v, 32 * c);
       }
       if (ck) {
         p.b1c[kidx * HID + j] = b1r;
         if (tid < 64) p.b2c[kidx * F + tid] = b2s[tid];  // b2s was updated by the same thread in P6
+      }
+      if (kTraj) {
+        p.b1img[((size_t)bh * p.img_slots + nstep) * HID + j] = b1r;
+        if (tid < 64) p.b2img[((size_t)bh * p.img_slots + nstep) * F + tid] = b2s[tid];
       }
       if (fin) {
         p.b1o[(size_t)bh * HID + j] = b1r;
@@ -508,17 +530,31 @@ int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) {
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, const void* XV, FwdParams& p, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv;
+  const uint64_t rows = (uint64_t)p.B * p.H * p.NC * CS;
+  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+  if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
+    return cudaErrorInvalidValue;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (traj) ttt_mlp_fwd_kernel<true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  else      ttt_mlp_fwd_kernel<false><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                const float* ln_b, const float* W1, const float* b1, const float* W2, const float* b2,
                                float* W1c, float* b1c, float* W2c, float* b2c, float* W1o, float* b1o, float* W2o,
                                float* b2o, void* Out, int B, int H, int NC, int ckpt_group, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || NC <= 0 || ckpt_group <= 0) return cudaErrorInvalidValue;
-  CUtensorMap tq, tk, tv;
-  const uint64_t rows = (uint64_t)B * H * NC * CS;
-  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-  if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
-    return cudaErrorInvalidValue;
-  FwdParams p;
+  FwdParams p{};
   p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
   p.ln_w = ln_w; p.ln_b = ln_b;
   p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
@@ -527,14 +563,24 @@ cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, c
   p.Out = reinterpret_cast<__nv_bfloat16*>(Out);
   p.B = B; p.H = H; p.NC = NC; p.ckpt_group = ckpt_group;
   p.K = (NC + ckpt_group - 1) / ckpt_group;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  ttt_mlp_fwd_kernel<<<B * H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
-  return cudaGetLastError();
+  p.t0 = 0; p.nsteps = NC; p.init_stride = 1; p.init_off = 0; p.img_slots = 0;
+  return launch_common(false, XQ, XK, XV, p, stream);
+}
+
+// Trajectory pass of the backward: recompute steps [t0, t0+nsteps) of every sequence from checkpoint `k` and save the
+// bf16 operand images of the nsteps+1 states (see FwdParams).  Checkpoint tensors are [B,H,K,...].
+cudaError_t launch_mlp_trajectory(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                  const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
+                                  const float* b2c, int B, int H, int NC, int K, int k, int t0, int nsteps,
+                                  uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream) {
+  FwdParams p{};
+  p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
+  p.ln_w = ln_w; p.ln_b = ln_b;
+  p.W1 = W1c; p.b1 = b1c; p.W2 = W2c; p.b2 = b2c;
+  p.B = B; p.H = H; p.NC = NC; p.ckpt_group = 1; p.K = K;
+  p.t0 = t0; p.nsteps = nsteps; p.init_stride = K; p.init_off = k; p.img_slots = img_slots;
+  p.img = img; p.b1img = b1img; p.b2img = b2img;
+  return launch_common(true, XK, XK, XV, p, stream);
 }
 
 }  // namespace tb

@@ -59,3 +59,71 @@ def ttt_forward(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1, b1, W2
 
 
 LAUNCHES_FWD = 1  # one persistent scan kernel per forward call
+_last_groups = [1]
+
+
+def launches_bwd():
+    """2 memsets are library calls; our kernels: one trajectory + one reverse launch per checkpoint group."""
+    return 2 * _last_groups[0]
+
+
+_ws_cache = {}
+
+
+def _workspace(B, H, G, device):
+    n = _lib.lib().ttt_b200_mlp_backward_workspace_bytes(B, H, G)
+    key = (device, n)
+    if key not in _ws_cache:
+        _ws_cache.clear()
+        _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=device)
+    return _ws_cache[key], n
+
+
+def ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkpoints, b1_checkpoints,
+                        W2_checkpoints, b2_checkpoints, grad_out, checkpoint_group_size):
+    """Backward with our own buffer management.  Returns, in TkMLP.backward order (mlp_tk.py:282-294):
+    (d ln_w [H,F], d ln_b [H,F], dW1 [B,H,F,4F], db1 [B,H,1,4F], dW2, db2, dXQ, dXV, dXK, d last_eta [B,H,NC,CS,1])."""
+    B, H, NC, CS, F = XQ.shape
+    dev = XQ.device
+    f32, bf = torch.float32, torch.bfloat16
+    K = (NC + checkpoint_group_size - 1) // checkpoint_group_size
+    _chk(grad_out, "grad_out", bf, (B, H, NC, CS, F))
+    _chk(W1_checkpoints, "W1_checkpoints", f32, (B, H, K, F, 4 * F))
+    dlw = torch.empty(B, H, F, device=dev, dtype=f32); dlb = torch.empty(B, H, F, device=dev, dtype=f32)
+    dW1 = torch.empty(B, H, F, 4 * F, device=dev, dtype=f32); db1 = torch.empty(B, H, 1, 4 * F, device=dev, dtype=f32)
+    dW2 = torch.empty(B, H, 4 * F, F, device=dev, dtype=f32); db2 = torch.empty(B, H, 1, F, device=dev, dtype=f32)
+    dq = torch.empty_like(XQ); dk = torch.empty_like(XQ); dv = torch.empty_like(XQ)
+    de = torch.empty(B, H, NC, CS, 1, device=dev, dtype=bf)
+    ws, n = _workspace(B, H, checkpoint_group_size, dev)
+    p = _lib.ptr
+    code = _lib.lib().ttt_b200_mlp_backward(
+        p(XQ), p(XK), p(XV), p(last_eta), p(ttt_norm_weight), p(ttt_norm_bias),
+        p(W1_checkpoints), p(b1_checkpoints), p(W2_checkpoints), p(b2_checkpoints), p(grad_out),
+        p(dlw), p(dlb), p(dW1), p(db1), p(dW2), p(db2), p(de), p(dq), p(dk), p(dv), p(ws), n,
+        B, H, NC, int(checkpoint_group_size), _lib.current_stream())
+    _lib.check(code, "ttt_b200_mlp_backward")
+    _last_groups[0] = K
+    return dlw.sum(0), dlb.sum(0), dW1, db1, dW2, db2, dq, dv, dk, de
+
+
+def ttt_backward(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkpoints, b1_checkpoints, W2_checkpoints,
+                 b2_checkpoints, Out, W1_init_group, b1_init_group, W2_init_group, b2_init_group, x_hat_ln_group,
+                 std_ln_group, X2_group, Z1_group, Z1_bar_group, X2_bar_group, grad_l_wrt_Z2_group, grad_l_wrt_Z1_group,
+                 x_hat_fused_group, grad_x_hat_fused_group, grad_output_fused_group, std_fused_group, grad_L_W1_last,
+                 grad_L_b1_last, grad_L_W2_last, grad_L_b2_last, grad_L_XQW_mini_batch, grad_L_ttt_norm_weight,
+                 grad_L_ttt_norm_bias, grad_L_W1_init, grad_L_b1_init, grad_L_W2_init, grad_L_b2_init, grad_L_last_eta,
+                 grad_L_XQ, grad_L_XK, grad_L_XV, checkpoint_group_size):
+    """test_time_training.ttt_backward with the reference's 43-argument signature (test_time_training.cpp:47-91).
+    The 16 re-materialisation buffers (args 12-27) are accepted and left untouched: this implementation keeps its
+    recompute state in a private L2-resident workspace.  Gradients are written in place into the caller's buffers
+    (the reference accumulates into pre-zeroed buffers, mlp_tk.py:213-225; writing gives the same result)."""
+    r = ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkpoints, b1_checkpoints,
+                            W2_checkpoints, b2_checkpoints, grad_L_XQW_mini_batch.to(torch.bfloat16).contiguous(),
+                            checkpoint_group_size)
+    B, H = XQ.shape[:2]
+    # per-batch LN gradients: the reference buffer is [B,H,1,F]; we already reduced over B -> put the sum in row 0
+    grad_L_ttt_norm_weight.zero_(); grad_L_ttt_norm_bias.zero_()
+    grad_L_ttt_norm_weight[0, :, 0, :] = r[0]; grad_L_ttt_norm_bias[0, :, 0, :] = r[1]
+    grad_L_W1_init.copy_(r[2]); grad_L_b1_init.copy_(r[3]); grad_L_W2_init.copy_(r[4]); grad_L_b2_init.copy_(r[5])
+    grad_L_XQ.copy_(r[6]); grad_L_XV.copy_(r[7]); grad_L_XK.copy_(r[8]); grad_L_last_eta.copy_(r[9])
+    return grad_L_XQ
