@@ -56,6 +56,21 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
                           void* workspace, size_t workspace_bytes,
                           int B, int H, int NC, int checkpoint_group_size, void* stream);
 
+/* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
+ * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in
+ * ttt/models/cogvideo/dit.py:90-103,213-222,241-266.  Tensors are bf16 [B, L, E], text tokens first
+ * (text_len = seq_text_length, split in num_chunks equal chunks), alpha f32 [E].
+ *   out[b,l,:] = res[b,l,:] + tanh(alpha(l)) * s[b, perm_s ? perm(l) : l, :]      alpha(l) = l < text_len ? text : video
+ *   if rev != NULL:  rev[b, perm(l), :] = out[b,l,:]                             (input of the reversed TTT pass)
+ * perm = text chunks in reverse order + video tokens flipped (an involution).  Backward: dres, ds (same layout as s),
+ * d_alpha_text / d_alpha_video f32 [E] (overwritten). */
+int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video,
+                          void* out, void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s,
+                          void* stream);
+int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, const float* alpha_text,
+                           const float* alpha_video, void* dres, void* ds, float* d_alpha_text, float* d_alpha_video,
+                           int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream);
+
 /* Debug/self-test: D[128][N] = A[128][K] . Bm[K][N] through one tcgen05 CTA (see csrc/umma_selftest.cu). */
 int ttt_b200_debug_umma(int mode, const void* A_bf16, const void* B_bf16, float* D, int N, int K, void* stream);
 

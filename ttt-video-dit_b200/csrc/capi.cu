@@ -6,6 +6,7 @@
 #include "ttt_internal.h"
 
 static thread_local char g_err[512] = "";
+namespace tb { thread_local const char* g_where = ""; }
 
 static int fail(int code, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s", what);
@@ -13,7 +14,7 @@ static int fail(int code, const char* what) {
 }
 static int cuda_ret(cudaError_t e, const char* where) {
   if (e == cudaSuccess) return 0;
-  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+  snprintf(g_err, sizeof(g_err), "%s [%s]: %s (%s)", where, tb::g_where, cudaGetErrorName(e), cudaGetErrorString(e));
   return (int)e;
 }
 
@@ -61,6 +62,24 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
                                           workspace, workspace_bytes, B, H, NC, checkpoint_group_size,
                                           (cudaStream_t)stream),
                   "ttt_b200_mlp_backward");
+}
+
+int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
+                          void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
+  if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");
+  return cuda_ret(tb::launch_gate_forward(res, s, alpha_text, alpha_video, out, rev, B, L, E, text_len, num_chunks,
+                                          perm_s, (cudaStream_t)stream),
+                  "ttt_b200_gate_forward");
+}
+
+int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, const float* alpha_text,
+                           const float* alpha_video, void* dres, void* ds, float* d_alpha_text, float* d_alpha_video,
+                           int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
+  if (!dout || !s || !alpha_text || !alpha_video || !dres || !ds || !d_alpha_text || !d_alpha_video)
+    return fail(-1, "ttt_b200_gate_backward: null pointer argument");
+  return cuda_ret(tb::launch_gate_backward(dout, drev, s, alpha_text, alpha_video, dres, ds, d_alpha_text,
+                                           d_alpha_video, B, L, E, text_len, num_chunks, perm_s, (cudaStream_t)stream),
+                  "ttt_b200_gate_backward");
 }
 
 int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N, int K, void* stream) {

@@ -6,6 +6,17 @@
 
 namespace tb {
 
+// last failing step inside a multi-launch entry point (read by capi.cu for the error message)
+extern thread_local const char* g_where;
+#define TB_TRY(call, what)                 \
+  do {                                     \
+    cudaError_t e__ = (call);              \
+    if (e__ != cudaSuccess) {              \
+      ::tb::g_where = (what);              \
+      return e__;                          \
+    }                                      \
+  } while (0)
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -32,4 +43,13 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
                                 const float* b2c, const void* dOut, float* dlnw, float* dlnb, float* dW1, float* db1,
                                 float* dW2, float* db2, void* dEta, void* dXQ, void* dXK, void* dXV, void* workspace,
                                 size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream);
+}  // namespace tb
+
+namespace tb {
+cudaError_t launch_gate_forward(const void* res, const void* s, const float* a_text, const float* a_video, void* out,
+                                void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s,
+                                cudaStream_t stream);
+cudaError_t launch_gate_backward(const void* dout, const void* drev, const void* s, const float* a_text,
+                                 const float* a_video, void* dres, void* ds, float* da_text, float* da_video, int B,
+                                 int L, int E, int text_len, int num_chunks, int perm_s, cudaStream_t stream);
 }  // namespace tb

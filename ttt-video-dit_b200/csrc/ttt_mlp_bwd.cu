@@ -802,8 +802,8 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
                                 const float* b2c, const void* dOut, float* dlnw, float* dlnb, float* dW1, float* db1,
                                 float* dW2, float* db2, void* dEta, void* dXQ, void* dXK, void* dXV, void* workspace,
                                 size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream) {
-  if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) return cudaErrorInvalidValue;
-  if (workspace_bytes < mlp_backward_workspace_bytes(B, H, G)) return cudaErrorInvalidValue;
+  if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) { g_where = "bad sizes"; return cudaErrorInvalidValue; }
+  if (workspace_bytes < mlp_backward_workspace_bytes(B, H, G)) { g_where = "workspace"; return cudaErrorInvalidValue; }
   const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   w = reinterpret_cast<uint8_t*>(((uintptr_t)w + 1023) & ~(uintptr_t)1023);
@@ -818,20 +818,16 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
 
   CUtensorMap tq, tk, tv, tdo;
   const uint64_t rows = (uint64_t)bh * NC * 64;
-  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+  if (rows > 0x7FFFFFFFull) { g_where = "too many rows"; return cudaErrorInvalidValue; }
   if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows) ||
-      make_token_tmap(&tdo, dOut, rows))
-    return cudaErrorInvalidValue;
+      make_token_tmap(&tdo, dOut, rows)) { g_where = "tensor map"; return cudaErrorInvalidValue; }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bwd::ttt_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SM_TOTAL);
-    if (e != cudaSuccess) return e;
+    TB_TRY(cudaFuncSetAttribute(bwd::ttt_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SM_TOTAL), "smem attr");
     attr_done = true;
   }
-  cudaError_t e = cudaMemsetAsync(dlnw, 0, bh * 64 * sizeof(float), stream);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(dlnb, 0, bh * 64 * sizeof(float), stream);
-  if (e != cudaSuccess) return e;
+  TB_TRY(cudaMemsetAsync(dlnw, 0, bh * 64 * sizeof(float), stream), "memset dlnw");
+  TB_TRY(cudaMemsetAsync(dlnb, 0, bh * 64 * sizeof(float), stream), "memset dlnb");
 
   const int K = (NC + G - 1) / G;
   for (int g = K - 1; g >= 0; --g) {
@@ -839,9 +835,8 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     const int t1 = (t0 + G < NC) ? t0 + G : NC;
     const bool last = (g == K - 1);
     // trajectory: images of W_{t0} .. W_{t1-1} (and W_NC for the last group)
-    e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0,
-                              last ? (t1 - t0) : (t1 - t0 - 1), img, b1img, b2img, (int)slots, stream);
-    if (e != cudaSuccess) return e;
+    TB_TRY(launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0,
+                                 last ? (t1 - t0) : (t1 - t0 - 1), img, b1img, b2img, (int)slots, stream), "trajectory launch");
     bwd::BwdParams p{};
     p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
     p.ln_w = ln_w; p.ln_b = ln_b;
@@ -857,8 +852,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.t_lo = t0; p.t0 = t0;
     p.first = last ? 1 : 0;
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, tdo, p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    TB_TRY(cudaGetLastError(), "reverse launch");
   }
   return cudaSuccess;
 }
