@@ -28,6 +28,23 @@ for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,2,4,2),(2,3,7,3),(1,4,33,16)]:
     print('fwd', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'per-step', per,
           'ck', [O.rel_err(a.cpu(), b) for a,b in zip(ck, rck)], 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
 """ % (ROOT, ROOT),
+    "bwd_direct": """
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from ttt_video_dit_b200 import test_time_training as tt
+from test_gpu_mlp_forward import run_forward
+d = O.make_inputs(1,1,1,seed=41)
+(q,k,v,le), out, ck, last = run_forward(d, 1)
+go = d['dOut'].to(torch.bfloat16).cuda()
+lw = d['ln_w'].float().cuda().reshape(1,1,1,64); lb = d['ln_b'].float().cuda().reshape(1,1,1,64)
+try:
+    r = tt.ttt_backward_simple(q,k,v,le,lw,lb,*ck,go,1)
+    torch.cuda.synchronize()
+    print('direct call ok', [float(x.float().abs().sum()) for x in r], flush=True)
+except Exception as ex:
+    print('direct EXC', repr(ex)[:600], flush=True)
+""" % (ROOT, ROOT),
     "bwd": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

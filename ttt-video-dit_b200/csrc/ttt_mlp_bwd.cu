@@ -820,7 +820,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   const uint64_t rows = (uint64_t)bh * NC * 64;
   if (rows > 0x7FFFFFFFull) { g_where = "too many rows"; return cudaErrorInvalidValue; }
   if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows) ||
-      make_token_tmap(&tdo, dOut, rows)) { g_where = "tensor map"; return cudaErrorInvalidValue; }
+      make_token_tmap(&tdo, dOut, rows)) return cudaErrorInvalidValue;  // g_where set by make_token_tmap
   static bool attr_done = false;
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(bwd::ttt_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SM_TOTAL), "smem attr");

@@ -518,8 +518,9 @@ static PFN_encodeTiled get_encode() {
 
 // 2-D bf16 tensor [rows][64], box [64 rows][64 cols], 128-B swizzle
 int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) {
+  static thread_local char detail[160];
   PFN_encodeTiled enc = get_encode();
-  if (!enc) return -1;
+  if (!enc) { g_where = "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed"; return -1; }
   cuuint64_t gdim[2] = {64, rows};
   cuuint64_t gstride[1] = {128};
   cuuint32_t box[2] = {64, 64};
@@ -527,7 +528,13 @@ int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) {
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -2;
+  if (r != CUDA_SUCCESS) {
+    snprintf(detail, sizeof(detail), "cuTensorMapEncodeTiled(base=%p, rows=%llu) -> CUresult %d", base,
+             (unsigned long long)rows, (int)r);
+    g_where = detail;
+    return -2;
+  }
+  return 0;
 }
 
 static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, const void* XV, FwdParams& p, cudaStream_t stream) {
@@ -536,6 +543,7 @@ static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, cons
   if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
   if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
     return cudaErrorInvalidValue;
+  g_where = "forward/trajectory launch";
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
