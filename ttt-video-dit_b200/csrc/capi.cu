@@ -1,4 +1,5 @@
 // extern "C" surface of libttt_b200.so (declared in include/ttt_b200.h).
+#include <cuda.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -16,6 +17,37 @@ static int cuda_ret(cudaError_t e, const char* where) {
   if (e == cudaSuccess) return 0;
   snprintf(g_err, sizeof(g_err), "%s [%s]: %s (%s)", where, tb::g_where, cudaGetErrorName(e), cudaGetErrorString(e));
   return (int)e;
+}
+
+// Bind the calling host thread to the device that owns `p`.  PyTorch's autograd worker threads (and any fresh thread)
+// have no current CUDA context in this library's (statically linked) runtime instance; driver calls such as
+// cuTensorMapEncodeTiled then fail with CUDA_ERROR_INVALID_CONTEXT and launches would go to device 0.
+typedef CUresult (*PFN_ptrAttr)(void*, CUpointer_attribute, CUdeviceptr);
+static int bind_device(const void* p) {
+  static PFN_ptrAttr fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_ptrAttr>(ptr);
+  }
+  int ord = -1;
+  if (!fn || fn(&ord, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS || ord < 0) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+      cudaGetLastError();
+      return fail(-5, "pointer argument is not a device pointer");
+    }
+    ord = a.device;
+  }
+  static thread_local int bound = -1;
+  if (bound != ord) {
+    cudaError_t e = cudaSetDevice(ord);
+    if (e != cudaSuccess) return cuda_ret(e, "cudaSetDevice");
+    bound = ord;
+  }
+  return 0;
 }
 
 extern "C" {
@@ -36,6 +68,7 @@ int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const v
   if (any_ck && !all_ck) return fail(-3, "ttt_b200_mlp_forward: checkpoint buffers must be all set or all NULL");
   const bool any_l = W1_last || b1_last || W2_last || b2_last, all_l = W1_last && b1_last && W2_last && b2_last;
   if (any_l && !all_l) return fail(-3, "ttt_b200_mlp_forward: final-state buffers must be all set or all NULL");
+  if (int rc = bind_device(XQ)) return rc;
   return cuda_ret(tb::launch_mlp_forward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1, b1, W2, b2, W1_ckpt, b1_ckpt,
                                          W2_ckpt, b2_ckpt, W1_last, b1_last, W2_last, b2_last, Out, B, H, NC,
                                          checkpoint_group_size, (cudaStream_t)stream),
@@ -57,6 +90,7 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
     return fail(-2, "ttt_b200_mlp_backward: B, H, NC and checkpoint_group_size must be positive");
   if (workspace_bytes < tb::mlp_backward_workspace_bytes(B, H, checkpoint_group_size))
     return fail(-4, "ttt_b200_mlp_backward: workspace too small (see ttt_b200_mlp_backward_workspace_bytes)");
+  if (int rc = bind_device(XQ)) return rc;
   return cuda_ret(tb::launch_mlp_backward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, W2_ckpt, b2_ckpt,
                                           dOut, d_ln_weight, d_ln_bias, dW1, db1, dW2, db2, d_last_eta, dXQ, dXK, dXV,
                                           workspace, workspace_bytes, B, H, NC, checkpoint_group_size,
@@ -67,6 +101,7 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");
+  if (int rc = bind_device(res)) return rc;
   return cuda_ret(tb::launch_gate_forward(res, s, alpha_text, alpha_video, out, rev, B, L, E, text_len, num_chunks,
                                           perm_s, (cudaStream_t)stream),
                   "ttt_b200_gate_forward");
@@ -77,12 +112,14 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                            int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!dout || !s || !alpha_text || !alpha_video || !dres || !ds || !d_alpha_text || !d_alpha_video)
     return fail(-1, "ttt_b200_gate_backward: null pointer argument");
+  if (int rc = bind_device(dout)) return rc;
   return cuda_ret(tb::launch_gate_backward(dout, drev, s, alpha_text, alpha_video, dres, ds, d_alpha_text,
                                            d_alpha_video, B, L, E, text_len, num_chunks, perm_s, (cudaStream_t)stream),
                   "ttt_b200_gate_backward");
 }
 
 int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N, int K, void* stream) {
+  if (int rc = bind_device(A)) return rc;
   return cuda_ret(tb::launch_umma_selftest(mode, A, Bm, D, N, K, (cudaStream_t)stream), "ttt_b200_debug_umma");
 }
 
