@@ -179,8 +179,9 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { r
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16.
 //   [4,6) c_format (1=f32) [7,10) a_format (1=bf16) [10,13) b_format [13] negA [14] negB [15] a_major (1 = MN)
 //   [16] b_major [17,23) N>>3 [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn, bool neg_a = false) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((neg_a ? 1u : 0u) << 13) | ((a_mn ? 1u : 0u) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn, bool neg_a = false,
+                                                       bool a_f16 = false, bool b_f16 = false) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((neg_a ? 1u : 0u) << 13) | ((a_mn ? 1u : 0u) << 15) |
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

@@ -17,8 +17,10 @@
 // from TMEM once per step.  All smem operand tiles use the SW128 row-tile convention of ptx.cuh.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "ttt_internal.h"
@@ -61,6 +63,30 @@ __device__ __forceinline__ float gelu_only(float z) {
   float t = tanh_fast(u);
   float hz = 0.5f * z;
   return fmaf(hz, t, hz);
+}
+
+// ---- packed-half GELU (2 elements per instruction on the FMA pipe, one MUFU.TANH per pair).  X2 is then stored as
+// fp16 (11-bit mantissa: tighter than the bf16 store of the fp32 path) and enters the MMAs as an F16 A operand next to
+// BF16 B operands (mixed kind::f16 formats, pinned by umma self-test modes 4/5).
+__device__ __forceinline__ __half2 h2_tanh(__half2 x) {
+  uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+  return *reinterpret_cast<__half2*>(&yi);
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 x) { return *reinterpret_cast<uint32_t*>(&x); }
+__device__ __forceinline__ uint32_t gelu_h2(float z0, float z1, __half2 b1h, uint32_t* grad_bits) {
+  const __half2 c0 = __float2half2_rn(0.79788456f), c1 = __float2half2_rn(0.79788456f * 0.044715f);
+  const __half2 c3 = __float2half2_rn(3.0f * 0.79788456f * 0.044715f), hh = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
+  const __half2 z = __hadd2(__floats2half2_rn(z0, z1), b1h);
+  const __half2 z2 = __hmul2(z, z);
+  const __half2 t = h2_tanh(__hmul2(z, __hfma2(c1, z2, c0)));
+  const __half2 hz = __hmul2(z, hh);
+  if (grad_bits) {
+    const __half2 s = __hfma2(__hneg2(t), t, one);
+    const __half2 g = __hfma2(__hmul2(hz, s), __hfma2(c3, z2, c0), __hfma2(hh, t, hh));
+    *grad_bits = h2_bits(g);
+  }
+  return h2_bits(__hfma2(hz, t, hz));
 }
 
 struct FwdParams {
@@ -107,7 +133,7 @@ __device__ __forceinline__ void store_row_bf16(uint32_t tile_saddr, int row, int
   }
 }
 
-template <bool kTraj>
+template <bool kTraj, bool kHalf>
 __global__ void __launch_bounds__(NT, 1)
 ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -192,7 +218,8 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   constexpr uint32_t IDESC_A = make_idesc_bf16(128, 128, false, false);  // D1: A K-major, B K-major
   constexpr uint32_t IDESC_A64 = make_idesc_bf16(128, 64, false, false);  // trajectory mode: K side only
-  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true);     // D2: A MN-major, B MN-major
+  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true, false, kHalf);  // D2: A (X2) MN-major, B MN-major
+  constexpr uint32_t IDESC_U2 = make_idesc_bf16(128, 64, false, true, false, kHalf);  // W2 update: A = X2^T
   constexpr uint32_t IDESC_C = make_idesc_bf16(128, 64, false, false);   // D3
   constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
 
@@ -247,21 +274,32 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t v[32];
         tmem_ld32(tsrc + 32 * c, v);
         tc_wait_ld();
-        if (c < 2) {
+        if (kHalf) {
+          const __half2 b1h = __float2half2_rn(b1r);
+          uint32_t o[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float g0, g1;
-            float x0 = gelu_and_grad(__uint_as_float(v[i]) + b1r, g0);
-            float x1 = gelu_and_grad(__uint_as_float(v[i + 1]) + b1r, g1);
-            v[i] = __float_as_uint(x0);
-            v[i + 1] = __float_as_uint(x1);
-            gp[16 * c + i / 2] = pack_bf16(g0, g1);
-          }
+          for (int i = 0; i < 32; i += 2)
+            o[i / 2] = gelu_h2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), b1h, c < 2 ? &gp[16 * c + i / 2] : nullptr);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(sbase + SM_X2 + (c >> 1) * 32768 + sw128_off(j, 4 * (c & 1) + q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         } else {
+          if (c < 2) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_only(__uint_as_float(v[i]) + b1r));
+            for (int i = 0; i < 32; i += 2) {
+              float g0, g1;
+              float x0 = gelu_and_grad(__uint_as_float(v[i]) + b1r, g0);
+              float x1 = gelu_and_grad(__uint_as_float(v[i + 1]) + b1r, g1);
+              v[i] = __float_as_uint(x0);
+              v[i + 1] = __float_as_uint(x1);
+              gp[16 * c + i / 2] = pack_bf16(g0, g1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_only(__uint_as_float(v[i]) + b1r));
+          }
+          store_row_bf16(sbase + SM_X2 + (c >> 1) * 32768, j, 4 * (c & 1), v);
         }
-        store_row_bf16(sbase + SM_X2 + (c >> 1) * 32768, j, 4 * (c & 1), v);
       }
     }
     fence_proxy_async();
@@ -399,7 +437,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint64_t da = make_desc_sw128(sbase + SM_X2 + h * 16384, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + TM_W2 + 64 * h, desc_advance(da, 32 * k), desc_advance(dg_mn, 2048 * k), IDESC_U, 1);
+          umma_ss(tmem + TM_W2 + 64 * h, desc_advance(da, 32 * k), desc_advance(dg_mn, 2048 * k), IDESC_U2, 1);
       }
     }
     mbar_wait(mma_bar, mma_phase);
@@ -417,8 +455,9 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float a0 = __uint_as_float(v[i]) * bf16_lo(gp[16 * c + i / 2]);
-          float a1 = __uint_as_float(v[i + 1]) * bf16_hi(gp[16 * c + i / 2]);
+          const uint32_t gpk = gp[16 * c + i / 2];
+          float a0 = __uint_as_float(v[i]) * (kHalf ? __low2float(*reinterpret_cast<const __half2*>(&gpk)) : bf16_lo(gpk));
+          float a1 = __uint_as_float(v[i + 1]) * (kHalf ? __high2float(*reinterpret_cast<const __half2*>(&gpk)) : bf16_hi(gpk));
           acc += a0 + a1;
           v[i] = __float_as_uint(a0);
           v[i + 1] = __float_as_uint(a1);
@@ -537,6 +576,16 @@ int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) {
   return 0;
 }
 
+static int g_half_gelu = -1;  // -1: read TTT_B200_HALF_GELU from the environment once
+static bool use_half_gelu() {
+  if (g_half_gelu < 0) {
+    const char* e = getenv("TTT_B200_HALF_GELU");
+    g_half_gelu = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_half_gelu != 0;
+}
+void set_half_gelu(int on) { g_half_gelu = on ? 1 : 0; }
+
 static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, const void* XV, FwdParams& p, cudaStream_t stream) {
   CUtensorMap tq, tk, tv;
   const uint64_t rows = (uint64_t)p.B * p.H * p.NC * CS;
@@ -546,14 +595,20 @@ static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, cons
   g_where = "forward/trajectory launch";
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e != cudaSuccess) return e;
+    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
+    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
+    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
+    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
     attr_done = true;
   }
-  if (traj) ttt_mlp_fwd_kernel<true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
-  else      ttt_mlp_fwd_kernel<false><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  const bool hg = use_half_gelu();
+  if (traj) {
+    if (hg) ttt_mlp_fwd_kernel<true, true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+    else    ttt_mlp_fwd_kernel<true, false><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  } else {
+    if (hg) ttt_mlp_fwd_kernel<false, true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+    else    ttt_mlp_fwd_kernel<false, false><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  }
   return cudaGetLastError();
 }
 

@@ -5,6 +5,8 @@
 //   mode 1: A MN-major (two 64-row blocks, LBO = K*128), B MN-major (N = 64)
 //   mode 2: A K-major,  B MN-major  (N = 64)
 //   mode 3: as mode 0 with K = 64 but B [N][64] is fetched by TMA (SWIZZLE_128B tensor map) instead of st.shared
+//   mode 4: as mode 0 but A holds fp16 bit patterns and B bf16 (mixed operand formats in one kind::f16 MMA)
+//   mode 5: as mode 1 (both MN-major) with A fp16 / B bf16
 #include "ptx.cuh"
 #include "ttt_internal.h"
 
@@ -35,7 +37,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
   for (int idx = tid; idx < 128 * K; idx += 128) {
     const int m = idx / K, k = idx % K;
     uint32_t off;
-    if (mode == 1) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
+    if (mode == 1 || mode == 5) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
     else           off = (uint32_t)(k >> 6) * 16384u + elem_off(m, k & 63);
     *reinterpret_cast<__nv_bfloat16*>(smem + off) = A[idx];
   }
@@ -44,7 +46,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
     for (int idx = tid; idx < K * N; idx += 128) {
       const int k = idx / N, n = idx % N;
       uint32_t off;
-      if (mode == 0) off = (uint32_t)(k >> 6) * (uint32_t)N * 128u + elem_off(n, k & 63);
+      if (mode == 0 || mode == 4) off = (uint32_t)(k >> 6) * (uint32_t)N * 128u + elem_off(n, k & 63);
       else           off = elem_off(k, n);
       *reinterpret_cast<__nv_bfloat16*>(smB + off) = Bm[idx];
     }
@@ -61,8 +63,8 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
   const uint32_t tmem = tmem_ptr;
 
   if (tid == 0) {
-    const bool a_mn = (mode == 1), b_mn = (mode == 1 || mode == 2);
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
+    const bool a_mn = (mode == 1 || mode == 5), b_mn = (mode == 1 || mode == 2 || mode == 5);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn, false, mode >= 4, false);
     for (int k16 = 0; k16 < K / 16; ++k16) {
       uint64_t da, db;
       if (a_mn) da = desc_advance(make_desc_sw128(sA, (uint32_t)K * 128u, 1024), 2048u * k16);
@@ -87,13 +89,13 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
 }
 
 cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float* D, int N, int K, cudaStream_t stream) {
-  if (mode < 0 || mode > 3 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
-  if ((mode == 1 || mode == 2) && N != 64) return cudaErrorInvalidValue;
+  if (mode < 0 || mode > 5 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
+  if ((mode == 1 || mode == 2 || mode == 5) && N != 64) return cudaErrorInvalidValue;
   if (mode == 3 && K != 64) return cudaErrorInvalidValue;
   CUtensorMap tm;
   // mode 3: Bm is given K-major already ([N][64] bf16); other modes do not dereference the map but it must be valid
   if (make_token_tmap(&tm, mode == 3 ? Bm : A, mode == 3 ? (uint64_t)N : 128ull)) return cudaErrorInvalidValue;
-  const size_t smem = 128 * (size_t)K * 2 + (size_t)((mode == 0 || mode == 3) ? N * K * 2 : K * 128);
+  const size_t smem = 128 * (size_t)K * 2 + (size_t)((mode == 0 || mode == 3 || mode == 4) ? N * K * 2 : K * 128);
   cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   umma_selftest_kernel<<<1, 128, smem, stream>>>(tm, mode, reinterpret_cast<const __nv_bfloat16*>(A),
