@@ -9,7 +9,7 @@ PROBES = {
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from test_gpu_umma import run_umma
-for mode, N, K in [(0,64,64),(0,128,64),(0,64,256),(3,64,64),(3,128,64),(2,64,64),(2,64,128),(1,64,64),(1,64,256)]:
+for mode, N, K in [(0,64,64),(0,128,64),(0,64,256),(3,64,64),(3,128,64),(2,64,64),(2,64,128),(1,64,64),(1,64,256),(4,64,64),(5,64,256),(6,64,256)]:
     try:
         print('umma mode', mode, 'N', N, 'K', K, 'relmax', run_umma(mode, N, K), flush=True)
     except Exception as e:
@@ -27,6 +27,19 @@ for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,2,4,2),(2,3,7,3),(1,4,33,16)]:
     per = [O.rel_err(out[:,:,n].float().cpu(), ref[:,:,n]) for n in range(min(NC,4))]
     print('fwd', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'per-step', per,
           'ck', [O.rel_err(a.cpu(), b) for a,b in zip(ck, rck)], 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
+""" % (ROOT, ROOT),
+    "fwd_half": """
+import os
+os.environ['TTT_B200_HALF_GELU'] = '1'
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from test_gpu_mlp_forward import run_forward, oracle_forward
+for (B,H,NC,G) in [(1,1,1,1),(1,2,4,2),(2,3,7,3),(1,4,33,16),(1,2,282,16)]:
+    d = O.make_inputs(B,H,NC,seed=10+NC)
+    qkve, out, ck, last = run_forward(d, G, want_last=True)
+    ref, rck, rlast = oracle_forward(qkve, d, G)
+    print('fwd_half', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
 """ % (ROOT, ROOT),
     "bwd_direct": """
 import torch, sys

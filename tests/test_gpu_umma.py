@@ -9,7 +9,9 @@ pytestmark = pytest.mark.gpu
 
 def run_umma(mode, N, K, seed=0):
     g = torch.Generator().manual_seed(seed)
-    A = torch.randn(128, K, generator=g).to(torch.float16 if mode >= 4 else torch.bfloat16).cuda()
+    A = torch.randn(128, K, generator=g).to(torch.float16 if mode in (4, 5) else torch.bfloat16).cuda()
+    if mode == 6:
+        A[64:] = A[:64]  # the kernel stages only rows 0-63; LBO = 0 must replicate them
     Bm = torch.randn(K, N, generator=g).to(torch.bfloat16).cuda()
     D = torch.zeros(128, N, device="cuda")
     b_arg = Bm.t().contiguous() if mode == 3 else Bm
@@ -21,6 +23,6 @@ def run_umma(mode, N, K, seed=0):
 
 
 @pytest.mark.parametrize("mode,N,K", [(0, 64, 64), (0, 128, 64), (0, 64, 256), (1, 64, 64), (1, 64, 256),
-                                      (2, 64, 64), (2, 64, 128), (3, 64, 64), (3, 128, 64), (4, 64, 64), (5, 64, 256)])
+                                      (2, 64, 64), (2, 64, 128), (3, 64, 64), (3, 128, 64), (4, 64, 64), (5, 64, 256), (6, 64, 256)])
 def test_umma_modes(mode, N, K):
     assert run_umma(mode, N, K) < 1e-5

@@ -33,8 +33,10 @@ constexpr uint32_t SM_TDO = 188416;    // dOut_{t-1}
 constexpr uint32_t SM_TT0 = 196608;    // dZ2 (K side) / dZbar2 (Q side)
 constexpr uint32_t SM_TT1 = 204800;    // gradZ2
 constexpr uint32_t SM_TT2 = 212992;    // -eta*gradZ2
-constexpr uint32_t SM_MISC = 221184;   // small fp32 vectors, barriers
-constexpr uint32_t SM_TOTAL = SM_MISC + 4096;  // 225280
+constexpr uint32_t SM_MISC = 221184;   // small fp32 vectors, barriers (2560 B)
+constexpr uint32_t SM_XB = SM_MISC + 2560;  // token-phase exchange buffers: float4[4][64], float2[4][64], float[4][64]
+constexpr uint32_t SM_TOTAL = SM_XB + 7168;  // 230912
+static_assert(SM_TOTAL <= 231424, "smem budget: 227 KB minus the 1 KB alignment slack of the dynamic window");
 
 // ---- TMEM columns
 constexpr uint32_t TM_DW1 = 0;    // dW1^T accumulator, + 64*h
@@ -125,6 +127,43 @@ __device__ __forceinline__ void warp_colsum(float* v, int lane) {
   }
 }
 
+// column sums of a per-lane vector v[16] over the 32 lanes: afterwards v[0] = sum over lanes of element ((lane >> 1) & 15)
+__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int m = 8; m >= 1; m >>= 1) {
+    const bool up = (lane & (2 * m)) != 0;  // lane bits 4..1 select the element, bit 0 is folded last
+#pragma unroll
+    for (int q = 0; q < m; ++q) {
+      const float a0 = v[q], b0 = v[q + m];
+      const float snd = up ? a0 : b0, kp = up ? b0 : a0;
+      v[q] = kp + __shfl_xor_sync(0xffffffffu, snd, 2 * m);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+// load 16 consecutive bf16 (two 16-B chunks c0, c0+1 of row r) from a SW128 tile
+__device__ __forceinline__ void ld_row16(uint32_t tile, int row, int chunk0, float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t a, b, cc, d;
+    ld_shared_v4(tile + sw128_off(row, chunk0 + c), a, b, cc, d);
+    v[8 * c + 0] = bf16_lo(a); v[8 * c + 1] = bf16_hi(a); v[8 * c + 2] = bf16_lo(b); v[8 * c + 3] = bf16_hi(b);
+    v[8 * c + 4] = bf16_lo(cc); v[8 * c + 5] = bf16_hi(cc); v[8 * c + 6] = bf16_lo(d); v[8 * c + 7] = bf16_hi(d);
+  }
+}
+__device__ __forceinline__ void st_row16(uint32_t tile, int row, int chunk0, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    st_shared_v4(tile + sw128_off(row, chunk0 + c), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+__device__ __forceinline__ void st_global16(__nv_bfloat16* g, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    *reinterpret_cast<uint4*>(g + 8 * c) = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                                                      pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+
 // ---- MMA issue helpers (single thread) -----------------------------------------------------------------------------
 // hidden-lane output: D[h] (128 lanes x N cols) = A_tile[h] (K-major, [256][64]) . B  ; 4 k-steps
 __device__ __forceinline__ void mma_hid(uint32_t d0, uint32_t d1, uint32_t a_tile, uint32_t b_tile, bool b_mn, int n,
@@ -139,11 +178,13 @@ __device__ __forceinline__ void mma_hid(uint32_t d0, uint32_t d1, uint32_t a_til
       umma_ss(h ? d1 : d0, desc_advance(da, 32 * k), desc_advance(db, b_mn ? 2048 * k : 32 * k), idesc, acc || k > 0);
   }
 }
-// token-lane output: D (rows 0-63 valid) = A_tile (hidden-lane tile viewed MN-major, [256 j][64 tok]) . B_tile ([256 j][64 f],
-// MN-major); 16 k-steps over the hidden dim.  Rows 64-127 of D come from whatever lies 32 KB after A_tile (never read).
+// token-lane output: D = A_tile (hidden-lane tile viewed MN-major, [256 j][64 tok]) . B_tile ([256 j][64 f], MN-major);
+// 16 k-steps over the hidden dim.  LBO = 0 makes the second 64-row block of A alias the first, so rows 64-127 of D are a
+// copy of rows 0-63: every token row is then readable from two TMEM lane halves and all 8 warps share the token phases
+// (thread <-> (row, 16-column quarter)); pinned by umma self-test mode 6.
 __device__ __forceinline__ void mma_tok(uint32_t d, uint32_t a_tile, uint32_t b_tile, bool acc) {
   const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
-  const uint64_t da = make_desc_sw128(a_tile, 32768, 1024);
+  const uint64_t da = make_desc_sw128(a_tile, 0, 1024);
   const uint64_t db = make_desc_sw128(b_tile, 1024, 1024);
 #pragma unroll
   for (int k = 0; k < 16; ++k) umma_ss(d, desc_advance(da, 2048 * k), desc_advance(db, 2048 * k), idesc, acc || k > 0);
@@ -178,8 +219,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* b2t = lnb + 64;      // b2 of W_t
   float* db2c = b2t + 64;     // d b2 carried (grad w.r.t. b2 after step t; updated in place during the iteration)
   float* etas = db2c + 64;    // eta of step t
-  float* etapart = etas + 64;  // [8 warps][64]: per-warp partial sums over hidden units for d eta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC + 3584);
+  float* etasum = etas + 64;  // sum over hidden units of gradZ1 * E (d eta), accumulated with shared atomics
+  float* dgam = etasum + 64;  // d gamma / d beta accumulated over the whole launch
+  float* dbet = dgam + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC + 2048);
   uint64_t* mma_bar = bars;       // tcgen05.commit
   uint64_t* bar_kv = bars + 1;    // K_t, V_t tiles
   uint64_t* bar_qd = bars + 2;    // Q_{t-1}, dO_{t-1} tiles
@@ -188,6 +231,14 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_w2 = bars + 5;    // W2 image
   uint64_t* bar_x2 = bars + 6;    // X2 tile reload
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float4* xA = reinterpret_cast<float4*>(smem + SM_XB);          // [4][64]
+  float2* xB = reinterpret_cast<float2*>(smem + SM_XB + 4096);   // [4][64]
+  float* epart = reinterpret_cast<float*>(smem + SM_XB + 6144);  // [4][64]
+  // token-phase mapping: thread <-> (row trow, column quarter cq); row r is read from TMEM lane r (warps with
+  // (warp&3) < 2) or from its duplicate at lane 64+r (the others) -- both inside this warp's own lane quarter.
+  const int trow = 32 * (warp & 1) + lane;
+  const int cq = 2 * (warp >> 2) + ((warp >> 1) & 1);
+  const int c0 = 16 * cq;
 
   if (tid == 0) {
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
@@ -199,6 +250,8 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     lnw[tid] = p.ln_w[head * 64 + tid];
     lnb[tid] = p.ln_b[head * 64 + tid];
     db2c[tid] = p.first ? 0.f : p.db2s[(size_t)bh * 64 + tid];
+    dgam[tid] = 0.f;
+    dbet[tid] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -226,7 +279,6 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
   uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
   uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0;
-  float dg_lo = 0.f, dg_hi = 0.f, dbt_lo = 0.f, dbt_hi = 0.f;  // d gamma / d beta partial sums of this lane (f = lane, lane+32)
 
   // first iteration's loads
   if (tid == 0) {
@@ -260,6 +312,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (tid < 64) {
       b2t[tid] = p.b2img[((size_t)bh * p.img_slots + slot) * F + tid];
       if (has_k) etas[tid] = __bfloat162float(p.last_eta[row_bh + (size_t)t * CS + tid]);
+      etasum[tid] = 0.f;
     }
     mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1;
     mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1;
@@ -323,58 +376,62 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         bulk_store_1d(p.x2spill + (size_t)bh * 32768, smem + sC, 32768);
         bulk_commit();
       }
-      // ===== A4 [T]: LN forward stats, gradZ2 -> TT1, -eta*gradZ2 -> TT2, dg2p = -eta(acc5+db2') -> S3, d eta partial
-      float e_acc = 0.f;
-      if (warp < 2) {
-        const int r = tid;
-        float z[64], tg[64];
+      // ===== A4 [T] (all warps; thread = (row, 16 columns)): LN stats of Z2, gradZ2 -> TT1, -eta*gradZ2 -> TT2,
+      //       dg2p = -eta(acc5 + db2') -> S3 (in place), partial of d eta
+      float ln_mu, ln_rstd, ln_s1, ln_s2;
+      {
+        float z[16], tg[16];
+        tmem_ld16(tmem + lane_addr + TM_S2 + c0, reinterpret_cast<uint32_t*>(z));
         {
-          float kk[64];
-          ld_row64(sbase + SM_TK, r, kk);
-          ld_row64(sbase + SM_TV, r, tg);
+          float kk[16];
+          ld_row16(sbase + SM_TK, trow, 2 * cq, kk);
+          ld_row16(sbase + SM_TV, trow, 2 * cq, tg);
 #pragma unroll
-          for (int f = 0; f < 64; ++f) tg[f] -= kk[f];
+          for (int f = 0; f < 16; ++f) tg[f] -= kk[f];  // target
         }
-        tmem_ld32(tmem + lane_addr + TM_S2, reinterpret_cast<uint32_t*>(z));
-        tmem_ld32(tmem + lane_addr + TM_S2 + 32, reinterpret_cast<uint32_t*>(z + 32));
         tc_wait_ld();
-        float mu = 0.f;
+        float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) { z[f] += b2t[f]; mu += z[f]; }
-        mu *= (1.f / 64.f);
-        float var = 0.f;
+        for (int f = 0; f < 16; ++f) { z[f] += b2t[c0 + f]; a1 += z[f]; a2 = fmaf(z[f], z[f], a2); }
+        xB[cq * 64 + trow] = make_float2(a1, a2);
+        __syncthreads();
+        a1 = 0.f; a2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
-        const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
+        for (int q = 0; q < 4; ++q) { const float2 v = xB[q * 64 + trow]; a1 += v.x; a2 += v.y; }
+        ln_mu = a1 * (1.f / 64.f);
+        ln_rstd = rsqrtf(fmaxf(a2 * (1.f / 64.f) - ln_mu * ln_mu, 0.f) + 1e-8f);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) {
-          z[f] *= rstd;                                          // x_hat
-          tg[f] = (fmaf(lnw[f], z[f], lnb[f]) - tg[f]) * lnw[f];  // gxh
+        for (int f = 0; f < 16; ++f) {
+          z[f] = (z[f] - ln_mu) * ln_rstd;                                          // x_hat
+          tg[f] = (fmaf(lnw[c0 + f], z[f], lnb[c0 + f]) - tg[f]) * lnw[c0 + f];      // gxh
           s1 += tg[f];
           s2 = fmaf(tg[f], z[f], s2);
         }
-        const float eta = etas[r];
+        xA[cq * 64 + trow] = make_float4(s1, s2, 0.f, 0.f);
+        __syncthreads();
+        s1 = 0.f; s2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) z[f] = (fmaf(64.f, tg[f], -s1) - z[f] * s2) * (rstd * (1.f / 64.f));  // gradZ2
-        st_row32(sbase + SM_TT1, r, 0, z);
-        st_row32(sbase + SM_TT1, r, 4, z + 32);
+        for (int q = 0; q < 4; ++q) { const float4 v = xA[q * 64 + trow]; s1 += v.x; s2 += v.y; }
+        ln_s1 = s1; ln_s2 = s2;
+        const float eta = etas[trow];
 #pragma unroll
-        for (int f = 0; f < 64; ++f) tg[f] = -eta * z[f];
-        st_row32(sbase + SM_TT2, r, 0, tg);
-        st_row32(sbase + SM_TT2, r, 4, tg + 32);
-        // acc5 -> dg2p (in place in S3), d eta partial
-        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(tg));
-        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(tg + 32));
+        for (int f = 0; f < 16; ++f) z[f] = (fmaf(64.f, tg[f], -s1) - z[f] * s2) * (ln_rstd * (1.f / 64.f));  // gradZ2
+        st_row16(sbase + SM_TT1, trow, 2 * cq, z);
+#pragma unroll
+        for (int f = 0; f < 16; ++f) tg[f] = -eta * z[f];
+        st_row16(sbase + SM_TT2, trow, 2 * cq, tg);
+        tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(tg));  // acc5
         tc_wait_ld();
+        float e = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) {
-          const float a = tg[f] + db2c[f];
-          e_acc = fmaf(-z[f], a, e_acc);
+        for (int f = 0; f < 16; ++f) {
+          const float a = tg[f] + db2c[c0 + f];
+          e = fmaf(-z[f], a, e);
           tg[f] = -eta * a;
         }
-        tmem_st32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(tg));
-        tmem_st32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(tg + 32));
+        epart[cq * 64 + trow] = e;
+        tmem_st16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(tg));
         tc_wait_st();
       }
       if (tid == 0) bulk_wait_read<0>();  // X2 tile has been read out of smem: slot sC may be overwritten
@@ -412,7 +469,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           st_row32(sbase + sW1, j, 4 * ch, raw);
           st_row32(sbase + sC, j, 4 * ch, pre);
           warp_colsum<32>(ep, lane);
-          etapart[warp * 64 + 32 * ch + lane] = ep[0];
+          atomicAdd(&etasum[32 * ch + lane], ep[0]);
         }
         PHASE_SYNC();
       }
@@ -431,103 +488,84 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_expect_tx(bar_x2, 32768);
         bulk_load_1d(smem + sC, p.x2spill + (size_t)bh * 32768, 32768, bar_x2);
       }
-      // ===== A8 [T]: stage 2 (backward through the fused LN + L2 gradient), dZ2 -> TT0, dV, d eta, fold -dtarget into S0
-      if (warp < 2) {
-        const int r = tid;
-        float z[64], dg[64], o[64];
-        tmem_ld32(tmem + lane_addr + TM_S2, reinterpret_cast<uint32_t*>(z));
-        tmem_ld32(tmem + lane_addr + TM_S2 + 32, reinterpret_cast<uint32_t*>(z + 32));
-        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(dg));
-        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(dg + 32));
+      // ===== A8 [T] (all warps): stage 2 = backward through the fused LN + L2 gradient (appendix B), dZ2 -> TT0, dV,
+      //       d eta, +dy (= -dtarget) folded into the dK accumulator S0, column sums for d b2 / d gamma / d beta
+      {
+        float z[16], go[16], dg[16];
+        tmem_ld16(tmem + lane_addr + TM_S2 + c0, reinterpret_cast<uint32_t*>(z));
+        tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(dg));
+        {
+          float kk[16];
+          ld_row16(sbase + SM_TK, trow, 2 * cq, kk);
+          ld_row16(sbase + SM_TV, trow, 2 * cq, go);
+#pragma unroll
+          for (int f = 0; f < 16; ++f) go[f] -= kk[f];  // target
+        }
         tc_wait_ld();
-        float mu = 0.f;
+        float sd = 0.f, sdx = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) { z[f] += b2t[f]; mu += z[f]; }
-        mu *= (1.f / 64.f);
-        float var = 0.f;
-#pragma unroll
-        for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
-        const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
-        float s1 = 0.f, s2 = 0.f, sd = 0.f, sdx = 0.f;
-        // pass 1: x_hat, go = gamma*xhat + beta - (V-K) kept in o[], row sums
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t kk[4], vv[4];
-          ld_shared_v4(sbase + SM_TK + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
-          ld_shared_v4(sbase + SM_TV + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int f = 8 * c + e;
-            const float tgt = (e & 1) ? (bf16_hi(vv[e >> 1]) - bf16_hi(kk[e >> 1])) : (bf16_lo(vv[e >> 1]) - bf16_lo(kk[e >> 1]));
-            z[f] *= rstd;
-            o[f] = fmaf(lnw[f], z[f], lnb[f]) - tgt;  // go
-            const float gxh = o[f] * lnw[f];
-            s1 += gxh;
-            s2 = fmaf(gxh, z[f], s2);
-            sd += dg[f];
-            sdx = fmaf(dg[f], z[f], sdx);
-          }
+        for (int f = 0; f < 16; ++f) {
+          z[f] = (z[f] + b2t[c0 + f] - ln_mu) * ln_rstd;                 // x_hat
+          go[f] = fmaf(lnw[c0 + f], z[f], lnb[c0 + f]) - go[f];           // grad_output
+          sd += dg[f];
+          sdx = fmaf(dg[f], z[f], sdx);
         }
-        // pass 2: d gamma contribution -> colsum ; sums of d_sigma and d_xhat
+        xB[cq * 64 + trow] = make_float2(sd, sdx);
+        __syncthreads();
+        sd = 0.f; sdx = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 v = xB[q * 64 + trow]; sd += v.x; sdx += v.y; }
         float sds = 0.f, sdxh = 0.f;
-        {
-          float cg[64];
+        float dy[16], cg[16];
 #pragma unroll
-          for (int f = 0; f < 64; ++f) {
-            const float gxh = o[f] * lnw[f];
-            const float gz2 = (fmaf(64.f, gxh, -s1) - z[f] * s2) * (rstd * (1.f / 64.f));
-            const float dgxh = rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
-            const float dy = lnw[f] * dgxh;
-            cg[f] = fmaf(o[f], dgxh, dy * z[f]);
-            const float dxh = fmaf(dy, lnw[f], -(rstd * (1.f / 64.f)) * fmaf(gxh, sdx, dg[f] * s2));
-            sds += (-dxh * z[f] - dg[f] * gz2) * rstd;
-            sdxh += dxh;
-          }
-          warp_colsum<64>(cg, lane);
-          dg_lo += cg[0]; dg_hi += cg[1];
+        for (int f = 0; f < 16; ++f) {
+          const float gam = lnw[c0 + f];
+          const float gxh = go[f] * gam;
+          const float gz2 = (fmaf(64.f, gxh, -ln_s1) - z[f] * ln_s2) * (ln_rstd * (1.f / 64.f));
+          const float dgxh = ln_rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
+          dy[f] = gam * dgxh;
+          cg[f] = fmaf(go[f], dgxh, dy[f] * z[f]);                                   // d gamma contribution
+          const float dxh = fmaf(dy[f], gam, -(ln_rstd * (1.f / 64.f)) * fmaf(gxh, sdx, dg[f] * ln_s2));
+          sds += (-dxh * z[f] - dg[f] * gz2) * ln_rstd;
+          sdxh += dxh;
+          dg[f] = dxh;                                                               // keep d_xhat
         }
-        // pass 3: dy -> dV (global), fold +dy into the dK accumulator S0, d beta colsum
-        {
-          float dy[64];
+        xA[cq * 64 + trow] = make_float4(sds, sdxh, 0.f, 0.f);
+        __syncthreads();
+        sds = 0.f; sdxh = 0.f;
 #pragma unroll
-          for (int f = 0; f < 64; ++f) dy[f] = lnw[f] * rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
-          __nv_bfloat16* gv = p.dXV + (row_bh + (size_t)t * CS + r) * F;
+        for (int q = 0; q < 4; ++q) { const float4 v = xA[q * 64 + trow]; sds += v.x; sdxh += v.y; }
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(gv + 8 * c) =
-                make_uint4(pack_bf16(-dy[8 * c], -dy[8 * c + 1]), pack_bf16(-dy[8 * c + 2], -dy[8 * c + 3]),
-                           pack_bf16(-dy[8 * c + 4], -dy[8 * c + 5]), pack_bf16(-dy[8 * c + 6], -dy[8 * c + 7]));
-          float a[32];
+        for (int f = 0; f < 16; ++f) dg[f] = fmaf(dg[f], ln_rstd, (1.f / 64.f) * (z[f] * sds - sdxh * ln_rstd));  // dZ2
+        st_row16(sbase + SM_TT0, trow, 2 * cq, dg);
+        {  // dV = dtarget = -dy
+          float nd[16];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tmem_ld32(tmem + lane_addr + TM_S0 + 32 * c, reinterpret_cast<uint32_t*>(a));
-            tc_wait_ld();
+          for (int f = 0; f < 16; ++f) nd[f] = -dy[f];
+          st_global16(p.dXV + (row_bh + (size_t)t * CS + trow) * F + c0, nd);
+        }
+        {  // fold -dtarget (= +dy) into the dK accumulator S0 (this thread's lane copy, its own 16 columns)
+          float a[16];
+          tmem_ld16(tmem + lane_addr + TM_S0 + c0, reinterpret_cast<uint32_t*>(a));
+          tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] += dy[32 * c + i];
-            tmem_st32(tmem + lane_addr + TM_S0 + 32 * c, reinterpret_cast<uint32_t*>(a));
-          }
+          for (int f = 0; f < 16; ++f) a[f] += dy[f];
+          tmem_st16(tmem + lane_addr + TM_S0 + c0, reinterpret_cast<uint32_t*>(a));
           tc_wait_st();
-          warp_colsum<64>(dy, lane);
-          dbt_lo += dy[0]; dbt_hi += dy[1];
         }
-        // pass 4: dZ2 -> TT0 tile, d b2 colsum
-#pragma unroll
-        for (int f = 0; f < 64; ++f) {
-          const float gxh = o[f] * lnw[f];
-          const float dy = lnw[f] * rstd * (dg[f] - (1.f / 64.f) * (sd + z[f] * sdx));
-          const float dxh = fmaf(dy, lnw[f], -(rstd * (1.f / 64.f)) * fmaf(gxh, sdx, dg[f] * s2));
-          o[f] = fmaf(dxh, rstd, (1.f / 64.f) * (z[f] * sds - sdxh * rstd));
+        if (cq == 0) {  // d eta of step t
+          const float e = epart[trow] + epart[64 + trow] + epart[128 + trow] + epart[192 + trow] - etasum[trow];
+          p.dEta[row_bh + (size_t)t * CS + trow] = __float2bfloat16(e);
         }
-        st_row32(sbase + SM_TT0, r, 0, o);
-        st_row32(sbase + SM_TT0, r, 4, o + 32);
-        warp_colsum<64>(o, lane);
-        atomicAdd(&db2c[lane], o[0]);
-        atomicAdd(&db2c[lane + 32], o[1]);
-        {  // d eta of step t
-          float e = e_acc;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) e -= etapart[w * 64 + r];
-          p.dEta[row_bh + (size_t)t * CS + r] = __float2bfloat16(e);
+        // column sums over this warp's 32 token rows (then shared atomics across the two row halves)
+        warp_colsum16(dg, lane);
+        warp_colsum16(cg, lane);
+        warp_colsum16(dy, lane);
+        if ((lane & 1) == 0) {
+          const int f = c0 + (lane >> 1);
+          atomicAdd(&db2c[f], dg[0]);
+          atomicAdd(&dgam[f], cg[0]);
+          atomicAdd(&dbet[f], dy[0]);
         }
       }
       PHASE_SYNC();
@@ -573,18 +611,11 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       MMA_WAIT();
       // ===== A12 [T]: dK -> global
-      if (warp < 2) {
-        const int r = tid;
-        float a[64];
-        tmem_ld32(tmem + lane_addr + TM_S0, reinterpret_cast<uint32_t*>(a));
-        tmem_ld32(tmem + lane_addr + TM_S0 + 32, reinterpret_cast<uint32_t*>(a + 32));
+      {
+        float a[16];
+        tmem_ld16(tmem + lane_addr + TM_S0 + c0, reinterpret_cast<uint32_t*>(a));
         tc_wait_ld();
-        __nv_bfloat16* gk = p.dXK + (row_bh + (size_t)t * CS + r) * F;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(gk + 8 * c) =
-              make_uint4(pack_bf16(a[8 * c], a[8 * c + 1]), pack_bf16(a[8 * c + 2], a[8 * c + 3]),
-                         pack_bf16(a[8 * c + 4], a[8 * c + 5]), pack_bf16(a[8 * c + 6], a[8 * c + 7]));
+        st_global16(p.dXK + (row_bh + (size_t)t * CS + trow) * F + c0, a);
       }
       tc_fence_before();
       __syncthreads();
@@ -638,44 +669,50 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
-      // ===== Q4 [T]: output LN backward: dZbar2 -> TT0 ; d gamma, d beta, d b2
-      if (warp < 2) {
-        const int r = tid;
-        float z[64], d[64];
-        ld_row64(sbase + SM_TDO, r, d);
-        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(z));
-        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(z + 32));
+      // ===== Q4 [T] (all warps): output LN backward: dZbar2 -> TT0 ; d gamma, d beta, d b2 column sums
+      {
+        float z[16], d[16];
+        tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(z));
+        ld_row16(sbase + SM_TDO, trow, 2 * cq, d);
         tc_wait_ld();
-        float mu = 0.f;
+        float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) { z[f] += b2t[f]; mu += z[f]; }
-        mu *= (1.f / 64.f);
-        float var = 0.f;
+        for (int f = 0; f < 16; ++f) { z[f] += b2t[c0 + f]; a1 += z[f]; a2 = fmaf(z[f], z[f], a2); }
+        xB[cq * 64 + trow] = make_float2(a1, a2);
+        __syncthreads();
+        a1 = 0.f; a2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
-        const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
+        for (int q = 0; q < 4; ++q) { const float2 v = xB[q * 64 + trow]; a1 += v.x; a2 += v.y; }
+        const float mu = a1 * (1.f / 64.f);
+        const float rstd = rsqrtf(fmaxf(a2 * (1.f / 64.f) - mu * mu, 0.f) + 1e-8f);
         float s1 = 0.f, s2 = 0.f;
-        float cg[64];
+        float cg[16];
 #pragma unroll
-        for (int f = 0; f < 64; ++f) {
-          z[f] *= rstd;
+        for (int f = 0; f < 16; ++f) {
+          z[f] = (z[f] - mu) * rstd;
           cg[f] = d[f] * z[f];               // d gamma contribution
-          const float dxh = d[f] * lnw[f];
+          const float dxh = d[f] * lnw[c0 + f];
           s1 += dxh;
           s2 = fmaf(dxh, z[f], s2);
         }
+        xA[cq * 64 + trow] = make_float4(s1, s2, 0.f, 0.f);
+        __syncthreads();
+        s1 = 0.f; s2 = 0.f;
 #pragma unroll
-        for (int f = 0; f < 64; ++f)
-          z[f] = (fmaf(64.f, d[f] * lnw[f], -s1) - z[f] * s2) * (rstd * (1.f / 64.f));  // dZbar2
-        st_row32(sbase + SM_TT0, r, 0, z);
-        st_row32(sbase + SM_TT0, r, 4, z + 32);
-        warp_colsum<64>(z, lane);
-        atomicAdd(&db2c[lane], z[0]);
-        atomicAdd(&db2c[lane + 32], z[1]);
-        warp_colsum<64>(cg, lane);
-        dg_lo += cg[0]; dg_hi += cg[1];
-        warp_colsum<64>(d, lane);
-        dbt_lo += d[0]; dbt_hi += d[1];
+        for (int q = 0; q < 4; ++q) { const float4 v = xA[q * 64 + trow]; s1 += v.x; s2 += v.y; }
+#pragma unroll
+        for (int f = 0; f < 16; ++f)
+          z[f] = (fmaf(64.f, d[f] * lnw[c0 + f], -s1) - z[f] * s2) * (rstd * (1.f / 64.f));  // dZbar2
+        st_row16(sbase + SM_TT0, trow, 2 * cq, z);
+        warp_colsum16(z, lane);
+        warp_colsum16(cg, lane);
+        warp_colsum16(d, lane);
+        if ((lane & 1) == 0) {
+          const int f = c0 + (lane >> 1);
+          atomicAdd(&db2c[f], z[0]);
+          atomicAdd(&dgam[f], cg[0]);
+          atomicAdd(&dbet[f], d[0]);
+        }
       }
       PHASE_SYNC();
       // ===== Q5 MMA: dX2bar^T = W2 . dZbar2^T -> (S1,S2) ; dW2 += X2bar^T dZbar2
@@ -720,19 +757,14 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       MMA_WAIT();
       // ===== Q8 [T]: dQ = dO + dQ_u
-      if (warp < 2) {
-        const int r = tid;
-        float a[64], d[64];
-        ld_row64(sbase + SM_TDO, r, d);
-        tmem_ld32(tmem + lane_addr + TM_S3, reinterpret_cast<uint32_t*>(a));
-        tmem_ld32(tmem + lane_addr + TM_S3 + 32, reinterpret_cast<uint32_t*>(a + 32));
+      {
+        float a[16], d[16];
+        tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(a));
+        ld_row16(sbase + SM_TDO, trow, 2 * cq, d);
         tc_wait_ld();
-        __nv_bfloat16* gq = p.dXQ + (row_bh + (size_t)(t - 1) * CS + r) * F;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(gq + 8 * c) = make_uint4(
-              pack_bf16(a[8 * c] + d[8 * c], a[8 * c + 1] + d[8 * c + 1]), pack_bf16(a[8 * c + 2] + d[8 * c + 2], a[8 * c + 3] + d[8 * c + 3]),
-              pack_bf16(a[8 * c + 4] + d[8 * c + 4], a[8 * c + 5] + d[8 * c + 5]), pack_bf16(a[8 * c + 6] + d[8 * c + 6], a[8 * c + 7] + d[8 * c + 7]));
+        for (int f = 0; f < 16; ++f) a[f] += d[f];
+        st_global16(p.dXQ + (row_bh + (size_t)(t - 1) * CS + trow) * F + c0, a);
       }
       tc_fence_before();
       __syncthreads();
@@ -777,11 +809,9 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     (fin ? p.db1 : p.db1s)[(size_t)bh * HID + j] = db1r;
     if (tid < 64) (fin ? p.db2 : p.db2s)[(size_t)bh * 64 + tid] = db2c[tid];
-    if (warp < 2) {
-      atomicAdd(&p.dlnw[(size_t)bh * 64 + lane], dg_lo);
-      atomicAdd(&p.dlnw[(size_t)bh * 64 + lane + 32], dg_hi);
-      atomicAdd(&p.dlnb[(size_t)bh * 64 + lane], dbt_lo);
-      atomicAdd(&p.dlnb[(size_t)bh * 64 + lane + 32], dbt_hi);
+    if (tid < 64) {
+      atomicAdd(&p.dlnw[(size_t)bh * 64 + tid], dgam[tid]);
+      atomicAdd(&p.dlnb[(size_t)bh * 64 + tid], dbet[tid]);
     }
   }
   tc_fence_before();

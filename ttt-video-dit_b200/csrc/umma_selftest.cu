@@ -7,6 +7,7 @@
 //   mode 3: as mode 0 with K = 64 but B [N][64] is fetched by TMA (SWIZZLE_128B tensor map) instead of st.shared
 //   mode 4: as mode 0 but A holds fp16 bit patterns and B bf16 (mixed operand formats in one kind::f16 MMA)
 //   mode 5: as mode 1 (both MN-major) with A fp16 / B bf16
+//   mode 6: as mode 1 but only rows 0-63 of A are staged and LBO = 0: rows 64-127 of D must duplicate rows 0-63
 #include "ptx.cuh"
 #include "ttt_internal.h"
 
@@ -37,7 +38,8 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
   for (int idx = tid; idx < 128 * K; idx += 128) {
     const int m = idx / K, k = idx % K;
     uint32_t off;
-    if (mode == 1 || mode == 5) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
+    if (mode == 6 && m >= 64) continue;
+    if (mode == 1 || mode == 5 || mode == 6) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
     else           off = (uint32_t)(k >> 6) * 16384u + elem_off(m, k & 63);
     *reinterpret_cast<__nv_bfloat16*>(smem + off) = A[idx];
   }
@@ -63,11 +65,11 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
   const uint32_t tmem = tmem_ptr;
 
   if (tid == 0) {
-    const bool a_mn = (mode == 1 || mode == 5), b_mn = (mode == 1 || mode == 2 || mode == 5);
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn, false, mode >= 4, false);
+    const bool a_mn = (mode == 1 || mode >= 5), b_mn = (mode == 1 || mode == 2 || mode >= 5);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn, false, mode == 4 || mode == 5, false);
     for (int k16 = 0; k16 < K / 16; ++k16) {
       uint64_t da, db;
-      if (a_mn) da = desc_advance(make_desc_sw128(sA, (uint32_t)K * 128u, 1024), 2048u * k16);
+      if (a_mn) da = desc_advance(make_desc_sw128(sA, mode == 6 ? 0u : (uint32_t)K * 128u, 1024), 2048u * k16);
       else      da = desc_advance(make_desc_sw128(sA + (k16 >> 2) * 16384u, 16, 1024), 32u * (k16 & 3));
       if (b_mn) db = desc_advance(make_desc_sw128(sB, 1024, 1024), 2048u * k16);
       else      db = desc_advance(make_desc_sw128(sB + (k16 >> 2) * (uint32_t)N * 128u, 16, 1024), 32u * (k16 & 3));
@@ -89,8 +91,8 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
 }
 
 cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float* D, int N, int K, cudaStream_t stream) {
-  if (mode < 0 || mode > 5 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
-  if ((mode == 1 || mode == 2 || mode == 5) && N != 64) return cudaErrorInvalidValue;
+  if (mode < 0 || mode > 6 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
+  if ((mode == 1 || mode == 2 || mode >= 5) && N != 64) return cudaErrorInvalidValue;
   if (mode == 3 && K != 64) return cudaErrorInvalidValue;
   CUtensorMap tm;
   // mode 3: Bm is given K-major already ([N][64] bf16); other modes do not dereference the map but it must be valid
