@@ -38,7 +38,8 @@ constexpr uint32_t SM_KQ = 131072;                // 2 slots x { K_t [64][64] ; 
 constexpr uint32_t SM_V = SM_KQ + 2 * 16384;      // 2 slots x V_t [64][64]
 constexpr uint32_t SM_G2 = SM_V + 2 * 8192;       // G2 = -eta*gradZ2 bf16 [64 tok][64]
 constexpr uint32_t SM_MISC = SM_G2 + 8192;        // b2[64] f32, ln_w[64], ln_b[64], barriers, tmem ptr
-constexpr uint32_t SM_TOTAL = SM_MISC + 1024;
+constexpr uint32_t SM_XB = SM_MISC + 1024;        // LN exchange: float2[2][128] + float2[2][64] + db2 accumulator[64]
+constexpr uint32_t SM_TOTAL = SM_XB + 4096;
 
 // TMEM column map (512 columns allocated)
 constexpr uint32_t TM_W1 = 0;    // + 64*h
@@ -65,9 +66,9 @@ __device__ __forceinline__ float gelu_only(float z) {
   return fmaf(hz, t, hz);
 }
 
-// ---- packed-half GELU (2 elements per instruction on the FMA pipe, one MUFU.TANH per pair).  X2 is then stored as
-// fp16 (11-bit mantissa: tighter than the bf16 store of the fp32 path) and enters the MMAs as an F16 A operand next to
-// BF16 B operands (mixed kind::f16 formats, pinned by umma self-test modes 4/5).
+// ---- packed-half GELU (2 elements per instruction on the FMA pipe, one MUFU.TANH per pair).  The result is converted
+// to bf16 for the X2 tile: a kind::f16 MMA with A = f16 and B = bf16 traps (illegal instruction) on sm_100a, measured
+// with umma self-test mode 4, so all MMA operands stay bf16.
 __device__ __forceinline__ __half2 h2_tanh(__half2 x) {
   uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
@@ -86,7 +87,8 @@ __device__ __forceinline__ uint32_t gelu_h2(float z0, float z1, __half2 b1h, uin
     const __half2 g = __hfma2(__hmul2(hz, s), __hfma2(c3, z2, c0), __hfma2(hh, t, hh));
     *grad_bits = h2_bits(g);
   }
-  return h2_bits(__hfma2(hz, t, hz));
+  const __half2 x = __hfma2(hz, t, hz);
+  return pack_bf16(__low2float(x), __high2float(x));
 }
 
 struct FwdParams {
@@ -151,6 +153,9 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* tma_bar = bars;      // [2]
   uint64_t* mma_bar = bars + 2;  // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  float2* xs1 = reinterpret_cast<float2*>(smem + SM_XB);         // [2][128]  (sum z, sum z^2) per column half
+  float2* xs2 = reinterpret_cast<float2*>(smem + SM_XB + 2048);  // [2][64]   (s1, s2) of the K side
+  float* db2acc = reinterpret_cast<float*>(smem + SM_XB + 3072);  // [64] column sums of G2, folded into b2 in P6
 
   if (tid == 0) {
     mbar_init(&tma_bar[0], 1);
@@ -166,6 +171,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     lnw[tid] = p.ln_w[head * 64 + tid];
     lnb[tid] = p.ln_b[head * 64 + tid];
     b2s[tid] = p.b2[((size_t)bh * p.init_stride + p.init_off) * 64 + tid];
+    db2acc[tid] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -218,8 +224,8 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   constexpr uint32_t IDESC_A = make_idesc_bf16(128, 128, false, false);  // D1: A K-major, B K-major
   constexpr uint32_t IDESC_A64 = make_idesc_bf16(128, 64, false, false);  // trajectory mode: K side only
-  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true, false, kHalf);  // D2: A (X2) MN-major, B MN-major
-  constexpr uint32_t IDESC_U2 = make_idesc_bf16(128, 64, false, true, false, kHalf);  // W2 update: A = X2^T
+  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true);  // D2: A (X2) MN-major, B MN-major
+  constexpr uint32_t IDESC_U2 = make_idesc_bf16(128, 64, false, true);  // W2 update: A = X2^T
   constexpr uint32_t IDESC_C = make_idesc_bf16(128, 64, false, false);   // D3
   constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
 
@@ -234,7 +240,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // prefetch eta for the LN threads of the K side
     float eta_i = 0.f;
-    if (has_k && warp < 2) eta_i = __bfloat162float(p.last_eta[row_base + (size_t)it * CS + tid]);
+    if (has_k && (warp & 3) < 2) eta_i = __bfloat162float(p.last_eta[row_base + (size_t)it * CS + 32 * (warp & 3) + lane]);
 
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
     if (tid == 0 && (kTraj ? (it + 1 < NC) : (it < NC))) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
@@ -320,93 +326,95 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mma_phase ^= 1;
     tc_fence_after();
 
-    // ---------------- P4: LayerNorm stage, one token row per thread (warps 0-3 own TMEM lanes 0-127)
-    if (warp < 4) {
-      const int row = tid;  // 0..63 K side, 64..127 Q side
+    // ---------------- P4: LayerNorm stage on all 8 warps: thread = (token row, 32-column half); warps w and w+4 share
+    //                  TMEM lanes, the row statistics are exchanged through smem (2 floats per exchange)
+    {
+      const int row = 32 * (warp & 3) + lane;  // 0..63 K side, 64..127 Q side
+      const int ch = warp >> 2;                // column half
       const bool kside = row < 64;
-      if ((kside && has_k) || (!kside && has_q)) {
-        float z[64];
-        {
-          uint32_t v[32];
-          tmem_ld32(tmem + lane_addr + TM_D2, v);
-          tc_wait_ld();
+      const bool active = kside ? has_k : has_q;
+      float z[32];
+      float mu = 0.f, rstd = 0.f;
+      if (active) {
+        tmem_ld32(tmem + lane_addr + TM_D2 + 32 * ch, reinterpret_cast<uint32_t*>(z));
+        tc_wait_ld();
+        float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(v[i]) + b2s[i];
-          tmem_ld32(tmem + lane_addr + TM_D2 + 32, v);
-          tc_wait_ld();
+        for (int i = 0; i < 32; ++i) { z[i] += b2s[32 * ch + i]; a1 += z[i]; a2 = fmaf(z[i], z[i], a2); }
+        xs1[ch * 128 + row] = make_float2(a1, a2);
+      }
+      __syncthreads();
+      if (active) {
+        const float2 p0 = xs1[row], p1 = xs1[128 + row];
+        mu = (p0.x + p1.x) * (1.0f / 64.0f);
+        rstd = rsqrtf(fmaxf((p0.y + p1.y) * (1.0f / 64.0f) - mu * mu, 0.f) + 1e-8f);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) z[32 + i] = __uint_as_float(v[i]) + b2s[32 + i];
-        }
-        float mu = 0.f;
+        for (int i = 0; i < 32; ++i) z[i] = (z[i] - mu) * rstd;  // x_hat
+      }
+      if (kside) {
+        // grad_out = gamma*xhat + beta - (V - K); gxh = grad_out*gamma
+        float g[32];
+        float s1 = 0.f, s2 = 0.f;
+        if (active) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mu += z[i];
-        mu *= (1.0f / 64.0f);
-        float var = 0.f;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          z[i] -= mu;
-          var = fmaf(z[i], z[i], var);
-        }
-        var *= (1.0f / 64.0f);
-        const float rstd = rsqrtf(var + 1e-8f);
-#pragma unroll
-        for (int i = 0; i < 64; ++i) z[i] *= rstd;  // x_hat
-        if (kside) {
-          // grad_out = gamma*xhat + beta - (V - K); gxh = grad_out*gamma
-          const int r = row;
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t kk[4], vv[4];
-            ld_shared_v4(kq + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
-            ld_shared_v4(vt + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
+            ld_shared_v4(kq + sw128_off(row, 4 * ch + c), kk[0], kk[1], kk[2], kk[3]);
+            ld_shared_v4(vt + sw128_off(row, 4 * ch + c), vv[0], vv[1], vv[2], vv[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int f = 8 * c + 2 * e;
-              float t0 = bf16_lo(vv[e]) - bf16_lo(kk[e]);
-              float t1 = bf16_hi(vv[e]) - bf16_hi(kk[e]);
-              float g0 = (fmaf(lnw[f], z[f], lnb[f]) - t0) * lnw[f];
-              float g1 = (fmaf(lnw[f + 1], z[f + 1], lnb[f + 1]) - t1) * lnw[f + 1];
-              s1 += g0 + g1;
-              s2 = fmaf(g0, z[f], s2);
-              s2 = fmaf(g1, z[f + 1], s2);
-              // stash gxh in place of nothing: recompute below needs z and g -> keep g in a second pass
-              // (registers: store g over kk/vv is not possible; we recompute g in pass 2)
+              const int i = 8 * c + 2 * e, f = 32 * ch + i;
+              const float t0 = bf16_lo(vv[e]) - bf16_lo(kk[e]);
+              const float t1 = bf16_hi(vv[e]) - bf16_hi(kk[e]);
+              g[i] = (fmaf(lnw[f], z[i], lnb[f]) - t0) * lnw[f];
+              g[i + 1] = (fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]) - t1) * lnw[f + 1];
+              s1 += g[i] + g[i + 1];
+              s2 = fmaf(g[i], z[i], s2);
+              s2 = fmaf(g[i + 1], z[i + 1], s2);
             }
           }
-          // pass 2: gradZ2 = (64*g - s1 - xhat*s2) / (64*std);  G2 = -eta * gradZ2
+          xs2[ch * 64 + row] = make_float2(s1, s2);
+        }
+        __syncthreads();
+        if (active) {
+          const float2 p0 = xs2[row], p1 = xs2[64 + row];
+          s1 = p0.x + p1.x; s2 = p0.y + p1.y;
+          // gradZ2 = (64*g - s1 - xhat*s2) / (64*std);  G2 = -eta * gradZ2
           const float sc = -eta_i * rstd * (1.0f / 64.0f);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t kk[4], vv[4], o[4];
-            ld_shared_v4(kq + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
-            ld_shared_v4(vt + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
+          for (int i = 0; i < 32; ++i) g[i] = (fmaf(64.0f, g[i], -s1) - z[i] * s2) * sc;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int f = 8 * c + 2 * e;
-              float t0 = bf16_lo(vv[e]) - bf16_lo(kk[e]);
-              float t1 = bf16_hi(vv[e]) - bf16_hi(kk[e]);
-              float g0 = (fmaf(lnw[f], z[f], lnb[f]) - t0) * lnw[f];
-              float g1 = (fmaf(lnw[f + 1], z[f + 1], lnb[f + 1]) - t1) * lnw[f + 1];
-              float d0 = (fmaf(64.0f, g0, -s1) - z[f] * s2) * sc;
-              float d1 = (fmaf(64.0f, g1, -s1) - z[f + 1] * s2) * sc;
-              o[e] = pack_bf16(d0, d1);
+          for (int c = 0; c < 4; ++c)
+            st_shared_v4(sbase + SM_G2 + sw128_off(row, 4 * ch + c), pack_bf16(g[8 * c], g[8 * c + 1]),
+                         pack_bf16(g[8 * c + 2], g[8 * c + 3]), pack_bf16(g[8 * c + 4], g[8 * c + 5]),
+                         pack_bf16(g[8 * c + 6], g[8 * c + 7]));
+          // b2 update = column sums of G2 over the 64 token rows (butterfly over the warp, then shared atomics)
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int q = 0; q < m; ++q) {
+              const float a0 = g[q], b0 = g[q + m];
+              g[q] = (up ? b0 : a0) + __shfl_xor_sync(0xffffffffu, up ? a0 : b0, m);
             }
-            st_shared_v4(sbase + SM_G2 + sw128_off(r, c), o[0], o[1], o[2], o[3]);
           }
-        } else {
+          atomicAdd(&db2acc[32 * ch + lane], g[0]);
+        }
+      } else {
+        __syncthreads();  // pairs with the K-side exchange barrier
+        if (active) {
           // output: O = Q + gamma*xhat + beta   (mini-batch it-1)
           const int r = row - 64;
-          __nv_bfloat16* og = p.Out + (row_base + (size_t)(it - 1) * CS + r) * F;
+          __nv_bfloat16* og = p.Out + (row_base + (size_t)(it - 1) * CS + r) * F + 32 * ch;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t qq[4], o[4];
-            ld_shared_v4(kq + 8192 + sw128_off(r, c), qq[0], qq[1], qq[2], qq[3]);
+            ld_shared_v4(kq + 8192 + sw128_off(r, 4 * ch + c), qq[0], qq[1], qq[2], qq[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int f = 8 * c + 2 * e;
-              float o0 = bf16_lo(qq[e]) + fmaf(lnw[f], z[f], lnb[f]);
-              float o1 = bf16_hi(qq[e]) + fmaf(lnw[f + 1], z[f + 1], lnb[f + 1]);
+              const int i = 8 * c + 2 * e, f = 32 * ch + i;
+              const float o0 = bf16_lo(qq[e]) + fmaf(lnw[f], z[i], lnb[f]);
+              const float o1 = bf16_hi(qq[e]) + fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]);
               o[e] = pack_bf16(o0, o1);
             }
             *reinterpret_cast<uint4*>(og + 8 * c) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -465,15 +473,9 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         store_row_bf16(sbase + SM_X2 + 32768, j, 4 * c, v);
       }
       b1r += acc;
-      if (tid < 64) {
-        float s = 0.f;
-        const int f = tid;
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) {
-          const __nv_bfloat16* rowp = reinterpret_cast<const __nv_bfloat16*>(smem + SM_G2 + sw128_off(i, f >> 3));
-          s += __bfloat162float(rowp[f & 7]);
-        }
-        b2s[f] += s;
+      if (tid < 64) {  // fold the column sums of G2 gathered in P4 into b2
+        b2s[tid] += db2acc[tid];
+        db2acc[tid] = 0.f;
       }
     }
     fence_proxy_async();
