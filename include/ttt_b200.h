@@ -56,6 +56,15 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
                           void* workspace, size_t workspace_bytes,
                           int B, int H, int NC, int checkpoint_group_size, void* stream);
 
+/* TTT-Linear forward scan (CS = 16, head_dim 64).  Replaces the Triton launch in ttt/models/ssm/linear_triton.py:96-131
+ * (kernel ttt/models/ssm/kernels/linear_forward.py:5-148).  XQ/XK/XV/Out bf16 [B,H,NC,16,64]; last_eta bf16 [B,H,NC,16];
+ * W1 f32 [B,H,64,64], b1 f32 [B,H,64]; checkpoints [B,H,K,64,64] / [B,H,K,64] (may be NULL); W1_last/b1_last as the
+ * reference's W1_last/b1_last outputs (may be NULL). */
+int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta,
+                            const float* ln_weight, const float* ln_bias, const float* W1, const float* b1,
+                            float* W1_ckpt, float* b1_ckpt, float* W1_last, float* b1_last, void* Out,
+                            int B, int H, int NC, int checkpoint_group_size, void* stream);
+
 /* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
  * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in
  * ttt/models/cogvideo/dit.py:90-103,213-222,241-266.  Tensors are bf16 [B, L, E], text tokens first

@@ -98,6 +98,20 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
                   "ttt_b200_mlp_backward");
 }
 
+int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_weight,
+                            const float* ln_bias, const float* W1, const float* b1, float* W1_ckpt, float* b1_ckpt,
+                            float* W1_last, float* b1_last, void* Out, int B, int H, int NC, int checkpoint_group_size,
+                            void* stream) {
+  if (!XQ || !XK || !XV || !last_eta || !ln_weight || !ln_bias || !W1 || !b1 || !Out)
+    return fail(-1, "ttt_b200_linear_forward: null pointer argument");
+  if ((W1_ckpt == nullptr) != (b1_ckpt == nullptr) || (W1_last == nullptr) != (b1_last == nullptr))
+    return fail(-3, "ttt_b200_linear_forward: W1/b1 buffer pairs must both be set or both be NULL");
+  if (int rc = bind_device(XQ)) return rc;
+  return cuda_ret(tb::launch_linear_forward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1, b1, W1_ckpt, b1_ckpt, W1_last,
+                                            b1_last, Out, B, H, NC, checkpoint_group_size, (cudaStream_t)stream),
+                  "ttt_b200_linear_forward");
+}
+
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");

@@ -22,6 +22,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows);
+int make_token_tmap_box(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows);
 
 cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                const float* ln_b, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -52,4 +53,11 @@ cudaError_t launch_gate_forward(const void* res, const void* s, const float* a_t
 cudaError_t launch_gate_backward(const void* dout, const void* drev, const void* s, const float* a_text,
                                  const float* a_video, void* dres, void* ds, float* da_text, float* da_video, int B,
                                  int L, int E, int text_len, int num_chunks, int perm_s, cudaStream_t stream);
+}  // namespace tb
+
+namespace tb {
+cudaError_t launch_linear_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                  const float* ln_b, const float* W1, const float* b1, float* W1c, float* b1c,
+                                  float* W1o, float* b1o, void* Out, int B, int H, int NC, int ckpt_group,
+                                  cudaStream_t stream);
 }  // namespace tb

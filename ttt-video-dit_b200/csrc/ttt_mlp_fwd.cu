@@ -557,14 +557,15 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows][64], box [64 rows][64 cols], 128-B swizzle
-int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) {
+// 2-D bf16 tensor [rows][64], box [box_rows][64 cols], 128-B swizzle
+int make_token_tmap(CUtensorMap* tm, const void* base, uint64_t rows) { return make_token_tmap_box(tm, base, rows, 64); }
+int make_token_tmap_box(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows) {
   static thread_local char detail[160];
   PFN_encodeTiled enc = get_encode();
   if (!enc) { g_where = "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed"; return -1; }
   cuuint64_t gdim[2] = {64, rows};
   cuuint64_t gstride[1] = {128};
-  cuuint32_t box[2] = {64, 64};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
