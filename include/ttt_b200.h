@@ -80,6 +80,10 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                            const float* alpha_video, void* dres, void* ds, float* d_alpha_text, float* d_alpha_video,
                            int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream);
 
+/* Debug: device buffer (>= 512 bytes) receiving per-phase cycle counts of block 0; returns 1 if this build was compiled
+ * with -DTTT_PHASE_TIMING (lib/libttt_b200_dbg.so), else 0 (the buffer is then never written). */
+int ttt_b200_debug_set_timing_buffer(void* dev_buf_512_bytes);
+
 /* Debug/self-test: D[128][N] = A[128][K] . Bm[K][N] through one tcgen05 CTA (see csrc/umma_selftest.cu). */
 int ttt_b200_debug_umma(int mode, const void* A_bf16, const void* B_bf16, float* D, int N, int K, void* stream);
 

@@ -41,6 +41,41 @@ for (B,H,NC,G) in [(1,1,1,1),(1,2,4,2),(2,3,7,3),(1,4,33,16),(1,2,282,16)]:
     ref, rck, rlast = oracle_forward(qkve, d, G)
     print('fwd_half', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
 """ % (ROOT, ROOT),
+    "timing": """
+import os
+os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from ttt_video_dit_b200 import _lib, mlp_tk
+buf = torch.zeros(128, dtype=torch.int32, device='cuda')
+print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
+B,H,NC,G = 1,48,64,16
+d = O.make_inputs(B,H,NC,seed=1)
+bf = lambda t: t.to(torch.bfloat16).cuda()
+prm = [d[k].cuda().requires_grad_(True) for k in ('ln_w','ln_b','W1','b1','W2','b2')]
+q,v,k = [bf(d[n]).requires_grad_(True) for n in ('XQ','XV','XK')]
+e = bf(d['eta'])[:,:,:,-1,:].clone().requires_grad_(True)
+for rep in range(2):
+    out = mlp_tk.ttt_mlp_op(*prm, q, v, k, e, G)
+    torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    names = ['top','tma_wait','P1 mma','P2 gelu','P3 mma','P4 LN','P5 mma','P6 gradZ1','P7 mma','P8 remat']
+    if rep == 1:
+        for ob in (0,1):
+            tot = sum(t[ob*64:ob*64+10])
+            print('FWD observer', ob, 'cycles/step total', tot/NC, {n: round(t[ob*64+i]/NC) for i,n in enumerate(names)}, flush=True)
+    buf.zero_()
+    out.backward(bf(d['dOut']))
+    torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    bn = ['top','A0 cw','A1 mma','A2 gelu3','A3 mma','A4 tok','A56 mma','A56 ew','A7 mma','A8 tok','A9 mma','A10 ew','A11 mma','A12 tok','Q1 mma','Q2 gelu','Q3 mma','Q4 tok','Q5 mma','Q6 ew','Q7 mma','Q8 tok']
+    if rep == 1:
+        for ob in (0,1):
+            tot = sum(t[ob*64:ob*64+22])
+            print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn)}, flush=True)
+    buf.zero_()
+""" % (ROOT, ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

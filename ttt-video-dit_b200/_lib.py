@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libttt_b200.so")
+LIB_PATH = os.environ.get("TTT_B200_LIB") or os.path.join(_HERE, "lib", "libttt_b200.so")
 _lib = None
 
 _vp, _fp, _i = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
@@ -18,6 +18,7 @@ _SIGS = {
     "ttt_b200_linear_forward": ([_vp] * 4 + [_fp] * 2 + [_fp] * 2 + [_fp] * 4 + [_vp] + [_i] * 4 + [_vp], ctypes.c_int),
     "ttt_b200_gate_forward": ([_vp, _vp, _fp, _fp, _vp, _vp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_gate_backward": ([_vp, _vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 6 + [_vp], ctypes.c_int),
+    "ttt_b200_debug_set_timing_buffer": ([_vp], ctypes.c_int),
     "ttt_b200_debug_umma": ([_i, _vp, _vp, _fp, _i, _i, _vp], ctypes.c_int),
 }
 

@@ -27,16 +27,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, dbg=False):
+    global LIB
+    if dbg:
+        return _build(os.path.join(LIBDIR, "libttt_b200_dbg.so"), os.path.join(HERE, "build_dbg"), ["-DTTT_PHASE_TIMING"], verbose)
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.path.join(HERE, "build"), [], verbose)
+
+
+def _build(LIB, objdir, extra, verbose):
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for s in sources():
         o = os.path.join(objdir, s[:-3] + ".o")
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     log = []
@@ -57,4 +63,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dbg="--dbg" in sys.argv))

@@ -7,7 +7,7 @@
 #include "ttt_internal.h"
 
 static thread_local char g_err[512] = "";
-namespace tb { thread_local const char* g_where = ""; }
+namespace tb { thread_local const char* g_where = ""; unsigned* g_timing_buf = nullptr; }
 
 static int fail(int code, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s", what);
@@ -130,6 +130,15 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
   return cuda_ret(tb::launch_gate_backward(dout, drev, s, alpha_text, alpha_video, dres, ds, d_alpha_text,
                                            d_alpha_video, B, L, E, text_len, num_chunks, perm_s, (cudaStream_t)stream),
                   "ttt_b200_gate_backward");
+}
+
+int ttt_b200_debug_set_timing_buffer(void* dev_buf_512_bytes) {
+  tb::g_timing_buf = reinterpret_cast<unsigned*>(dev_buf_512_bytes);
+#ifdef TTT_PHASE_TIMING
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N, int K, void* stream) {

@@ -8,6 +8,31 @@
 #include <stdint.h>
 #include <stdio.h>
 
+// Phase timing (debug builds only: -DTTT_PHASE_TIMING -> lib/libttt_b200_dbg.so).  TICK(i) adds the cycles since the
+// previous TICK to slot i for two observer threads of block 0; the kernel epilogue dumps the slots to tb::g_timing_buf.
+#ifdef TTT_PHASE_TIMING
+#define TICK_DECL(NSLOT, OBS_B)                                                                         \
+  const int tick_obs = (blockIdx.x == 0 && threadIdx.x == 0) ? 0 : ((blockIdx.x == 0 && threadIdx.x == (OBS_B)) ? 1 : -1); \
+  unsigned tick_acc[NSLOT];                                                                             \
+  _Pragma("unroll") for (int i_ = 0; i_ < (NSLOT); ++i_) tick_acc[i_] = 0;                             \
+  unsigned tick_last = clock();
+#define TICK(i)                          \
+  do {                                   \
+    const unsigned now_ = clock();       \
+    tick_acc[i] += now_ - tick_last;     \
+    tick_last = now_;                    \
+  } while (0)
+#define TICK_DUMP(NSLOT, buf)                                                                              \
+  do {                                                                                                     \
+    if (tick_obs >= 0 && (buf) != nullptr)                                                                 \
+      _Pragma("unroll") for (int i_ = 0; i_ < (NSLOT); ++i_)(buf)[tick_obs * 64 + i_] = tick_acc[i_];   \
+  } while (0)
+#else
+#define TICK_DECL(NSLOT, OBS_B)
+#define TICK(i)
+#define TICK_DUMP(NSLOT, buf)
+#endif
+
 namespace tb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

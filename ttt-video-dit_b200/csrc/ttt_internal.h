@@ -8,6 +8,7 @@ namespace tb {
 
 // last failing step inside a multi-launch entry point (read by capi.cu for the error message)
 extern thread_local const char* g_where;
+extern unsigned* g_timing_buf;  // device buffer [2][64] for phase timing (debug builds), may be null
 #define TB_TRY(call, what)                 \
   do {                                     \
     cudaError_t e__ = (call);              \

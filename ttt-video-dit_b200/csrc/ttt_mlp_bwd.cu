@@ -56,6 +56,7 @@ struct BwdParams {
   int H, NC, img_slots;
   int t_hi, t_lo, t0;  // iterations t_hi..t_lo (descending); image slot of W_t is t - t0
   int first;           // 1: start from zero state gradient, 0: load it from the scratch
+  unsigned* dbg;       // phase-timing buffer (debug builds)
 };
 
 __device__ __forceinline__ void gelu3(float z, float& g0, float& g1, float& g2) {
@@ -303,6 +304,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
 
+  TICK_DECL(22, 224)
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
   for (int t = p.t_hi; t >= p.t_lo; --t) {
@@ -319,6 +321,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (has_k) { mbar_wait(bar_kv, ph_kv); ph_kv ^= 1; }
     if (has_q) { mbar_wait(bar_qd, ph_qd); ph_qd ^= 1; }
     __syncthreads();  // b2t / etas visible
+      TICK(0);
 
     if (has_k) {
       // ===== A0 [H]: bf16 copies of the carried gradient accumulators: CW1 -> sA, CW2 -> sB
@@ -335,6 +338,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       PHASE_SYNC();
+      TICK(1);
       // ===== A1 MMA: R1 = W1 . K^T -> (S0,S1)
       if (tid == 0) {
         tc_fence_after();
@@ -342,6 +346,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(2);
       // ===== A2 [H]: Z1 -> X2 tile (sC), gelu', gelu''
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S1 : TM_S0);
@@ -363,6 +368,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       PHASE_SYNC();
+      TICK(3);
       // ===== A3 MMA: R2: Z2 = X2 . W2 -> S2 ; B5: acc5 = X2 . CW2 -> S3
       if (tid == 0) {
         tc_fence_after();
@@ -371,6 +377,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(4);
       // spill the X2 tile to L2 (needed again by the dW2 += X2^T dZ2 GEMM at the end of the K side)
       if (tid == 0) {
         bulk_store_1d(p.x2spill + (size_t)bh * 32768, smem + sC, 32768);
@@ -436,6 +443,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (tid == 0) bulk_wait_read<0>();  // X2 tile has been read out of smem: slot sC may be overwritten
       PHASE_SYNC();
+      TICK(5);
 
       // ===== A5/A6 (two chunks of 32 tokens): pre = W2 . gradZ2^T -> S0, raw = CW1 . K^T -> S1 (N = 32);
       //       [H]: gradZ1, d gradZ1, DG1 -> sW1, G1eta -> sC, term2, d eta hidden-sums
@@ -448,6 +456,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_commit(mma_bar);
         }
         MMA_WAIT();
+      TICK(6);
         {
           float pre[32], raw[32];
           tmem_ld32(tmem + lane_addr + TM_S0 + 32 * half, reinterpret_cast<uint32_t*>(pre));
@@ -472,6 +481,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           atomicAdd(&etasum[32 * ch + lane], ep[0]);
         }
         PHASE_SYNC();
+      TICK(7);
       }
       // ===== A7 MMA: dK acc: S0 = G1eta . CW1 ; S3 += DG1 . W2
       if (tid == 0) {
@@ -481,6 +491,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(8);
       if (tid == 0) {  // sA (CW1) and sC (G1eta) are free: reload the W1 image and the X2 tile
         bulk_wait<0>();
         mbar_expect_tx(bar_w1r, 32768);
@@ -569,6 +580,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       PHASE_SYNC();
+      TICK(9);
       // ===== A9 MMA: dX2^T = W2 . dZ2^T + CW2 . (-eta gradZ2)^T -> (S1,S2)
       if (tid == 0) {
         tc_fence_after();
@@ -577,6 +589,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(10);
       // ===== A10 [H]: dZ1 = dX2 * gelu'(Z1) + term2 -> sB ; d b1 += sum dZ1
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
@@ -600,6 +613,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_w1r, ph_w1r); ph_w1r ^= 1;
       mbar_wait(bar_x2, ph_x2); ph_x2 ^= 1;
       PHASE_SYNC();
+      TICK(11);
       // ===== A11 MMA: dK: S0 += dZ1 . W1 ; dW2 += DG1^T gradZ2 + X2^T dZ2 ; dW1^T += dZ1^T K
       if (tid == 0) {
         tc_fence_after();
@@ -610,6 +624,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(12);
       // ===== A12 [T]: dK -> global
       {
         float a[16];
@@ -619,6 +634,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       tc_fence_before();
       __syncthreads();
+      TICK(13);
     } else {
       // Q-only iteration (t == NC): the W1 image sits in sW1; the Q chain below expects it in sA
       const uint32_t tmp = sA; sA = sW1; sW1 = tmp;
@@ -643,6 +659,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(14);
       // ===== Q2 [H]: X2bar -> sB, gelu'(Zbar1)
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
@@ -662,6 +679,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       PHASE_SYNC();
+      TICK(15);
       // ===== Q3 MMA: Zbar2 = X2bar . W2 -> S3
       if (tid == 0) {
         tc_fence_after();
@@ -669,6 +687,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(16);
       // ===== Q4 [T] (all warps): output LN backward: dZbar2 -> TT0 ; d gamma, d beta, d b2 column sums
       {
         float z[16], d[16];
@@ -715,6 +734,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       PHASE_SYNC();
+      TICK(17);
       // ===== Q5 MMA: dX2bar^T = W2 . dZbar2^T -> (S1,S2) ; dW2 += X2bar^T dZbar2
       if (tid == 0) {
         tc_fence_after();
@@ -723,6 +743,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(18);
       if (tid == 0 && more) {  // W2 image buffer is free: fetch the next one
         mbar_expect_tx(bar_w2, 32768);
         bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
@@ -748,6 +769,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         db1r += acc;
       }
       PHASE_SYNC();
+      TICK(19);
       // ===== Q7 MMA: dW1^T += dZbar1^T Q ; dQ_u = dZbar1 . W1 -> S3
       if (tid == 0) {
         tc_fence_after();
@@ -756,6 +778,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_commit(mma_bar);
       }
       MMA_WAIT();
+      TICK(20);
       // ===== Q8 [T]: dQ = dO + dQ_u
       {
         float a[16], d[16];
@@ -768,6 +791,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       tc_fence_before();
       __syncthreads();
+      TICK(21);
     } else if (tid == 0 && more) {  // (cannot happen: t == 0 is always the last iteration) keep the W2 prefetch paired
       mbar_expect_tx(bar_w2, 32768);
       bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
@@ -785,6 +809,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   }
 
+  TICK_DUMP(22, p.dbg);
   // ---- epilogue: carried gradient -> scratch (or final outputs), LN parameter gradients
   tc_fence_after();
   {
@@ -881,6 +906,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.t_hi = last ? NC : t1 - 1;
     p.t_lo = t0; p.t0 = t0;
     p.first = last ? 1 : 0;
+    p.dbg = (g == 0) ? g_timing_buf : nullptr;  // time the last launch (a full group)
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, tdo, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
   }

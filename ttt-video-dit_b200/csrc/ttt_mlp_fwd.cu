@@ -106,6 +106,7 @@ struct FwdParams {
   int t0, nsteps, init_stride, init_off, img_slots;
   uint8_t* img;
   float *b1img, *b2img;
+  unsigned* dbg;  // phase-timing buffer (debug builds)
 };
 
 // store one thread's state rows (fp32, still in registers) to a [64][256] W1 image and a [256][64] W2 image
@@ -230,6 +231,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
 
   uint32_t mma_phase = 0;
+  TICK_DECL(12, 224)
   uint32_t gp[32];  // gelu'(Z1) for this thread's hidden unit, 64 tokens, packed bf16x2
 
   for (int it = 0; it < (kTraj ? NC : NC + 1); ++it) {
@@ -242,7 +244,9 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float eta_i = 0.f;
     if (has_k && (warp & 3) < 2) eta_i = __bfloat162float(p.last_eta[row_base + (size_t)it * CS + 32 * (warp & 3) + lane]);
 
+    TICK(0);
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
+    TICK(1);
     if (tid == 0 && (kTraj ? (it + 1 < NC) : (it < NC))) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
       const int ns = slot ^ 1;
       const bool nk = (it + 1) < NC;
@@ -270,6 +274,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    TICK(2);
 
     // ---------------- P2: gelu on D1 row j -> X2^T / X2bar^T (bf16, SW128 rows); keep gelu'(Z1)
     {
@@ -311,6 +316,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    TICK(3);
 
     // ---------------- P3: D2 = [X2 ; X2bar] . W2b   (M=128 tokens, N=64, K=256 hidden; both operands MN-major)
     if (tid == 0) {
@@ -325,6 +331,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    TICK(4);
 
     // ---------------- P4: LayerNorm stage on all 8 warps: thread = (token row, 32-column half); warps w and w+4 share
     //                  TMEM lanes, the row statistics are exchanged through smem (2 floats per exchange)
@@ -426,6 +433,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    TICK(5);
 
     // ---------------- P5: D3[h] = W2b[h] . G2^T  (critical) ;  W2[h] += X2^T[h] . G2  (off the critical path)
     if (tid == 0) {
@@ -451,6 +459,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    TICK(6);
 
     // ---------------- P6: G1^T row j = D3 row j * gelu'(Z1) (bf16) ; b1 += sum ; threads 0-63: b2 += column sums of G2
     {
@@ -481,6 +490,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    TICK(7);
 
     // ---------------- P7: W1^T[h] += G1^T[h] . K
     if (tid == 0) {
@@ -498,6 +508,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    TICK(8);
 
     // ---------------- P8: re-materialise bf16 operand copies of the new state (+ checkpoint / final state)
     {
@@ -536,7 +547,9 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    TICK(9);
   }
+  TICK_DUMP(12, p.dbg);
 
   tc_fence_before();
   __syncthreads();
@@ -604,6 +617,7 @@ static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, cons
     TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
     attr_done = true;
   }
+  p.dbg = traj ? nullptr : g_timing_buf;
   const bool hg = use_half_gelu();
   if (traj) {
     if (hg) ttt_mlp_fwd_kernel<true, true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
