@@ -307,14 +307,29 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   TICK_DECL(22, 224)
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
+  float nb1 = p.b1img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * HID + j], nb2 = 0.f;
+  unsigned short neta = 0;
+  if (tid < 64) {
+    nb2 = p.b2img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * F + tid];
+    if (p.t_hi < p.NC) neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)p.t_hi * CS + tid];
+  }
   for (int t = p.t_hi; t >= p.t_lo; --t) {
     const bool has_k = t < p.NC, has_q = t > 0;
     const size_t slot = (size_t)(t - p.t0);
-    const float b1t = p.b1img[((size_t)bh * p.img_slots + slot) * HID + j];
+    // per-iteration small vectors were prefetched into registers during the previous iteration (nb1/nb2/neta)
+    const float b1t = nb1;
     if (tid < 64) {
-      b2t[tid] = p.b2img[((size_t)bh * p.img_slots + slot) * F + tid];
-      if (has_k) etas[tid] = __bfloat162float(p.last_eta[row_bh + (size_t)t * CS + tid]);
+      b2t[tid] = nb2;
+      if (has_k) etas[tid] = __uint_as_float((uint32_t)neta << 16);
       etasum[tid] = 0.f;
+    }
+    if (t > p.t_lo) {  // prefetch for iteration t-1 (always a K iteration)
+      const size_t ns = slot - 1;
+      nb1 = p.b1img[((size_t)bh * p.img_slots + ns) * HID + j];
+      if (tid < 64) {
+        nb2 = p.b2img[((size_t)bh * p.img_slots + ns) * F + tid];
+        neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)(t - 1) * CS + tid];
+      }
     }
     mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1;
     mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1;
@@ -849,7 +864,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------------------ host
 size_t mlp_backward_workspace_bytes(int B, int H, int G) {
   const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
-  return bh * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4 + 2 * 65536 + 1024 + 256 + 32768) + 1024;
+  return bh * (2 * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + 2 * 65536 + 1024 + 256 + 32768) + 1024;
 }
 
 cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
@@ -862,12 +877,16 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   w = reinterpret_cast<uint8_t*>(((uintptr_t)w + 1023) & ~(uintptr_t)1023);
-  uint8_t* img = w;                      w += bh * slots * 65536;
+  uint8_t* img[2]; float *b1img[2], *b2img[2];   // ping-pong: trajectory(g-1) overlaps reverse(g) on a side stream
+  img[0] = w;                            w += bh * slots * 65536;
+  img[1] = w;                            w += bh * slots * 65536;
   uint8_t* x2s = w;                      w += bh * 32768;
   float* dW1s = reinterpret_cast<float*>(w); w += bh * 65536;
   float* dW2s = reinterpret_cast<float*>(w); w += bh * 65536;
-  float* b1img = reinterpret_cast<float*>(w); w += bh * slots * 1024;
-  float* b2img = reinterpret_cast<float*>(w); w += bh * slots * 256;
+  b1img[0] = reinterpret_cast<float*>(w); w += bh * slots * 1024;
+  b1img[1] = reinterpret_cast<float*>(w); w += bh * slots * 1024;
+  b2img[0] = reinterpret_cast<float*>(w); w += bh * slots * 256;
+  b2img[1] = reinterpret_cast<float*>(w); w += bh * slots * 256;
   float* db1s = reinterpret_cast<float*>(w); w += bh * 1024;
   float* db2s = reinterpret_cast<float*>(w); w += bh * 256;
 
@@ -884,18 +903,44 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   TB_TRY(cudaMemsetAsync(dlnw, 0, bh * 64 * sizeof(float), stream), "memset dlnw");
   TB_TRY(cudaMemsetAsync(dlnb, 0, bh * 64 * sizeof(float), stream), "memset dlnb");
 
+  // side stream + events (one set per device, created once)
+  struct Side { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, evT[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr}; };
+  static Side sides[64];
+  int dev = 0;
+  TB_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  Side& sd = sides[dev & 63];
+  if (!sd.s) {
+    TB_TRY(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking), "side stream");
+    TB_TRY(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming), "event");
+    for (int i = 0; i < 2; ++i) {
+      TB_TRY(cudaEventCreateWithFlags(&sd.evT[i], cudaEventDisableTiming), "event");
+      TB_TRY(cudaEventCreateWithFlags(&sd.evR[i], cudaEventDisableTiming), "event");
+    }
+  }
   const int K = (NC + G - 1) / G;
+  auto traj = [&](int g) -> cudaError_t {  // images of W_{t0} .. W_{t1-1} (and W_NC for the last group) into buffer g&1
+    const int t0 = g * G;
+    const int t1 = (t0 + G < NC) ? t0 + G : NC;
+    const bool last = (g == K - 1);
+    cudaError_t e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0,
+                                          last ? (t1 - t0) : (t1 - t0 - 1), img[g & 1], b1img[g & 1], b2img[g & 1],
+                                          (int)slots, sd.s);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(sd.evT[g & 1], sd.s);
+  };
+  TB_TRY(cudaEventRecord(sd.fork, stream), "fork record");
+  TB_TRY(cudaStreamWaitEvent(sd.s, sd.fork, 0), "fork wait");
+  TB_TRY(traj(K - 1), "trajectory launch");
+  if (K > 1) TB_TRY(traj(K - 2), "trajectory launch");
   for (int g = K - 1; g >= 0; --g) {
     const int t0 = g * G;
     const int t1 = (t0 + G < NC) ? t0 + G : NC;
     const bool last = (g == K - 1);
-    // trajectory: images of W_{t0} .. W_{t1-1} (and W_NC for the last group)
-    TB_TRY(launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0,
-                                 last ? (t1 - t0) : (t1 - t0 - 1), img, b1img, b2img, (int)slots, stream), "trajectory launch");
+    TB_TRY(cudaStreamWaitEvent(stream, sd.evT[g & 1], 0), "wait trajectory");
     bwd::BwdParams p{};
     p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
     p.ln_w = ln_w; p.ln_b = ln_b;
-    p.img = img; p.b1img = b1img; p.b2img = b2img;
+    p.img = img[g & 1]; p.b1img = b1img[g & 1]; p.b2img = b2img[g & 1];
     p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
     p.x2spill = x2s;
     p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
@@ -909,6 +954,11 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.dbg = (g == 0) ? g_timing_buf : nullptr;  // time the last launch (a full group)
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, tdo, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
+    if (g >= 2) {  // buffer g&1 is free again once this reverse launch is done: recompute group g-2 into it
+      TB_TRY(cudaEventRecord(sd.evR[g & 1], stream), "record reverse");
+      TB_TRY(cudaStreamWaitEvent(sd.s, sd.evR[g & 1], 0), "wait reverse");
+      TB_TRY(traj(g - 2), "trajectory launch");
+    }
   }
   return cudaSuccess;
 }

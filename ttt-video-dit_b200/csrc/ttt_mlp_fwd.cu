@@ -231,6 +231,21 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
 
   uint32_t mma_phase = 0;
+  auto issue_p1 = [&](int it_next) {  // thread 0 only: wait for the tiles of iteration it_next, then D1 = W1b^T . [K|Q]^T
+    const int sl = it_next & 1;
+    mbar_wait(&tma_bar[sl], (it_next >> 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t da = make_desc_sw128(sbase + SM_W1B + h * 16384, 16, 1024);
+      const uint64_t db = make_desc_sw128(sbase + SM_KQ + sl * 16384, 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), kTraj ? IDESC_A64 : IDESC_A, k > 0);
+    }
+    tc_commit(mma_bar);
+  };
+  if (tid == 0 && NC > 0) issue_p1(0);
   TICK_DECL(12, 224)
   uint32_t gp[32];  // gelu'(Z1) for this thread's hidden unit, 64 tokens, packed bf16x2
 
@@ -241,8 +256,11 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t vt = sbase + SM_V + slot * 8192;
 
     // prefetch eta for the LN threads of the K side
-    float eta_i = 0.f;
-    if (has_k && (warp & 3) < 2) eta_i = __bfloat162float(p.last_eta[row_base + (size_t)it * CS + 32 * (warp & 3) + lane]);
+    // eta of this step for the K-side LN rows: fetched as raw bf16 bits here, converted at the point of use (P4) so the
+    // global-load latency hides behind P1-P3 instead of stalling the warp at the top of the iteration
+    unsigned short eta_raw = 0;
+    if (has_k && (warp & 3) < 2)
+      eta_raw = reinterpret_cast<const unsigned short*>(p.last_eta)[row_base + (size_t)it * CS + 32 * (warp & 3) + lane];
 
     TICK(0);
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
@@ -258,19 +276,8 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (!kTraj) tma_load_2d(smem + SM_KQ + ns * 16384 + 8192, &tmQ, 0, (int)(row_base + (size_t)it * CS), &tma_bar[ns]);
     }
 
-    // ---------------- P1: D1[h] = W1b^T[h] . [K | Q]^T   (M=128, N=128, K=64)
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint64_t da = make_desc_sw128(sbase + SM_W1B + h * 16384, 16, 1024);
-        const uint64_t db = make_desc_sw128(kq, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), kTraj ? IDESC_A64 : IDESC_A, k > 0);
-      }
-      tc_commit(mma_bar);
-    }
+    // ---------------- P1: D1[h] = W1b^T[h] . [K | Q]^T  (M=128, N=128, K=64) -- issued early, at the end of the
+    //                  previous iteration's P8 (or in the prologue), so it overlaps the W2 re-materialisation
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
@@ -387,6 +394,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float2 p0 = xs2[row], p1 = xs2[64 + row];
           s1 = p0.x + p1.x; s2 = p0.y + p1.y;
           // gradZ2 = (64*g - s1 - xhat*s2) / (64*std);  G2 = -eta * gradZ2
+          const float eta_i = __uint_as_float((uint32_t)eta_raw << 16);
           const float sc = -eta_i * rstd * (1.0f / 64.0f);
 #pragma unroll
           for (int i = 0; i < 32; ++i) g[i] = (fmaf(64.0f, g[i], -s1) - z[i] * s2) * sc;
@@ -525,6 +533,15 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         store_row_bf16(sbase + SM_W1B, j, 4 * c, v, imgs);
         if (ck) store_w1_col(p.W1c + kidx * F * HID, j, v, 32 * c);
         if (fin) store_w1_col(p.W1o + (size_t)bh * F * HID, j, v, 32 * c);
+      }
+      // W1b is complete: start the next iteration's D1 now, it runs under the W2 conversion below
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0 && (kTraj ? (it + 1 < NC) : true)) issue_p1(it + 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
         tmem_ld32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
         tc_wait_ld();
         store_row_bf16(sbase + SM_W2B, j, 4 * c, v, imgs ? imgs + 32768 : nullptr);
