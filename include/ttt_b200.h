@@ -65,6 +65,13 @@ int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, cons
                             float* W1_ckpt, float* b1_ckpt, float* W1_last, float* b1_last, void* Out,
                             int B, int H, int NC, int checkpoint_group_size, void* stream);
 
+/* Non-causal self-attention forward over one segment, head_dim 64.  Replaces F.scaled_dot_product_attention(q, k, v,
+ * attn_mask=None, dropout_p=0, is_causal=False) at ttt/models/cogvideo/dit.py:196-198.  q/k/v/out: bf16 [B, T, H, 64]
+ * contiguous = the "b t (h d)" output of the q/k/v Linears, so the reference's rearranges around SDPA disappear.
+ * scale = 1/sqrt(64) for the reference's call. */
+int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void* out, int B, int T, int H,
+                               float scale, void* stream);
+
 /* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
  * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in
  * ttt/models/cogvideo/dit.py:90-103,213-222,241-266.  Tensors are bf16 [B, L, E], text tokens first

@@ -112,6 +112,14 @@ int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, cons
                   "ttt_b200_linear_forward");
 }
 
+int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void* out, int B, int T, int H, float scale,
+                               void* stream) {
+  if (!q || !k || !v || !out) return fail(-1, "ttt_b200_attention_forward: null pointer argument");
+  if (int rc = bind_device(q)) return rc;
+  return cuda_ret(tb::launch_attention_forward(q, k, v, out, B, T, H, scale, (cudaStream_t)stream),
+                  "ttt_b200_attention_forward");
+}
+
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");

@@ -62,3 +62,8 @@ cudaError_t launch_linear_forward(const void* XQ, const void* XK, const void* XV
                                   float* W1o, float* b1o, void* Out, int B, int H, int NC, int ckpt_group,
                                   cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, int B, int T, int H,
+                                     float scale, cudaStream_t stream);
+}  // namespace tb
