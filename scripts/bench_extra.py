@@ -1,0 +1,78 @@
+"""Secondary measurements (not the driver's bench contract): TTT-Linear forward, local attention forward vs the library
+SDPA the reference calls, gate kernels vs the HBM roofline.  One JSON line per kernel.  CUDA-event timing, 3 warm-ups."""
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.nn.functional as F
+
+import __graft_entry__
+
+__graft_entry__.build()
+from ttt_video_dit_b200 import attention, linear_triton, seq_block
+
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+dev = "cuda"
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_attention(T=18048, H=48, B=1):
+    q, k, v = (torch.randn(B, T, H, 64, device=dev, dtype=torch.bfloat16) for _ in range(3))
+    ms = timeit(lambda: attention.sdpa_bthd(q, k, v))
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    ms_lib = timeit(lambda: F.scaled_dot_product_attention(qh, kh, vh, is_causal=False))
+    flop = 4.0 * T * T * 64 * H * B
+    print(json.dumps({"kernel": "attn_fwd_kernel", "shape": [B, T, H, 64], "ms": ms, "tflops": flop / ms / 1e9,
+                      "frac_of_bf16_peak": flop / ms / 1e9 / peaks["bf16_tflops"],
+                      "library_sdpa_ms": ms_lib, "library_sdpa_tflops": flop / ms_lib / 1e9, "speed_vs_library": ms_lib / ms}))
+
+
+def bench_linear(NC=1128, H=48, B=1):
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    q = F.normalize(r(B, H, NC, 16, 64), dim=-1).to(torch.bfloat16).to(dev)
+    k = F.normalize(r(B, H, NC, 16, 64), dim=-1).to(torch.bfloat16).to(dev)
+    v = r(B, H, NC, 16, 64).to(torch.bfloat16).to(dev)
+    le = ((1.0 / 64) * torch.sigmoid(r(B, H, NC, 16)) / 16).to(torch.bfloat16).to(dev)
+    lw, lb = (1 + 0.1 * r(H, 64)).to(dev), (0.1 * r(H, 64)).to(dev)
+    W1 = (0.02 * r(B, H, 64, 64)).to(dev); b1 = torch.zeros(B, H, 1, 64, device=dev)
+    ms = timeit(lambda: linear_triton.linear_forward(q, k, v, le, lw, lb, W1, b1, 16))
+    flop = 3 * 2 * 16 * 64 * 64 * NC * H * B
+    print(json.dumps({"kernel": "ttt_linear_fwd_kernel", "shape": [B, H, NC, 16, 64], "ms": ms, "tokens_per_s": B * NC * 16 / ms * 1e3,
+                      "tflops": flop / ms / 1e9, "us_per_minibatch": ms * 1e3 / NC}))
+
+
+def bench_gate(L=18048, E=3072, B=1):
+    x = torch.randn(B, L, E, device=dev, dtype=torch.bfloat16)
+    s = torch.randn(B, L, E, device=dev, dtype=torch.bfloat16)
+    a = [0.1 * torch.ones(E, device=dev) for _ in range(2)]
+    ms = timeit(lambda: seq_block.GatedResidual.apply(x, s, a[0], a[1], 498, 1, False, True))
+    bytes_ = 4 * x.numel() * 2  # read res, s; write out, rev
+    print(json.dumps({"kernel": "gate_fwd_kernel<false,true>", "shape": [B, L, E], "ms": ms, "GBps": bytes_ / ms / 1e6,
+                      "frac_of_hbm_peak": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["attention", "linear", "gate"]
+    if "attention" in which:
+        bench_attention()
+    if "linear" in which:
+        bench_linear()
+    if "gate" in which:
+        bench_gate()
