@@ -43,7 +43,7 @@ for (B,H,NC,G) in [(1,1,1,1),(1,2,4,2),(2,3,7,3),(1,4,33,16),(1,2,282,16)]:
 """ % (ROOT, ROOT),
     "timing": """
 import os
-os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+os.environ['TTT_B200_LIB'] = os.environ.get('TTT_B200_TIMING_LIB', %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so')
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
@@ -69,10 +69,10 @@ for rep in range(2):
     out.backward(bf(d['dOut']))
     torch.cuda.synchronize()
     t = buf.cpu().tolist()
-    bn = ['top','A0 cw','A1 mma','A2 gelu3','A3 mma','A4 tok','A56 mma','A56 ew','A7 mma','A8 tok','A9 mma','A10 ew','A11 mma','A12 tok','Q1 mma','Q2 gelu','Q3 mma','Q4 tok','Q5 mma','Q6 ew','Q7 mma','Q8 tok']
+    bn = ['top','apply+A0 cw','A1 mma','A2 gelu3','A3 mma','A4 tok','A56 mma','A56 ew','A7 mma','A8 tok','A9 mma','A10 ew','A11 mma','A12 tok']
     if rep == 1:
         for ob in (0,1):
-            tot = sum(t[ob*64:ob*64+22])
+            tot = sum(t[ob*64:ob*64+14])
             print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn)}, flush=True)
     buf.zero_()
 """ % (ROOT, ROOT, ROOT),

@@ -52,7 +52,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qt * BM;
+  // No out-of-bounds TMA boxes: the last query / key tile is shifted back to end exactly at T (T >= 128 is required);
+  // rows it shares with the previous tile are masked (keys) or recomputed identically (queries).
+  const int q0 = min(qt * BM, T - BM);
   const int ntiles = (T + BN - 1) / BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC);
   uint64_t* bar_q = bars;        // Q tile
@@ -75,7 +77,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = *tmem_ptr;
   const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
 
-  if (tid == 0) {  // TMA zero-fills rows beyond T (out-of-bounds box elements)
+  if (tid == 0) {
     mbar_expect_tx(bar_q, 16384);
     tma_load_4d(smem + SM_Q, &tmQ, 0, h, q0, b, bar_q);
     mbar_expect_tx(&bar_kv[0], 32768);
@@ -95,8 +97,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (tid == 0) {
       if (j + 1 < ntiles) {  // the other slot was released by the PV MMA of tile j-1 (waited below)
         mbar_expect_tx(&bar_kv[slot ^ 1], 32768);
-        tma_load_4d(smem + SM_K + (slot ^ 1) * 16384, &tmK, 0, h, (j + 1) * BN, b, &bar_kv[slot ^ 1]);
-        tma_load_4d(smem + SM_V + (slot ^ 1) * 16384, &tmV, 0, h, (j + 1) * BN, b, &bar_kv[slot ^ 1]);
+        const int kb = min((j + 1) * BN, T - BN);
+        tma_load_4d(smem + SM_K + (slot ^ 1) * 16384, &tmK, 0, h, kb, b, &bar_kv[slot ^ 1]);
+        tma_load_4d(smem + SM_V + (slot ^ 1) * 16384, &tmV, 0, h, kb, b, &bar_kv[slot ^ 1]);
       }
       // S = Q . K_j^T
       tc_fence_after();
@@ -111,8 +114,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
 
     // ---- online softmax for this thread's query row
-    const int kbase = j * BN;
-    const int nvalid = T - kbase;  // keys >= T are padding
+    const int kbase = min(j * BN, T - BN);
+    const int first_new = j * BN - kbase;  // keys below this index were already consumed by the previous tile
     float mx = m_run;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -121,7 +124,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float v = (32 * c + i < nvalid) ? s[i] * scale_log2 : -INFINITY;
+        const float v = (32 * c + i >= first_new) ? s[i] * scale_log2 : -INFINITY;
         mx = fmaxf(mx, v);
       }
     }
@@ -134,7 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float pexp = (32 * c + i < nvalid) ? ex2(fmaf(s[i], scale_log2, -mx)) : 0.f;
+        const float pexp = (32 * c + i >= first_new) ? ex2(fmaf(s[i], scale_log2, -mx)) : 0.f;
         lsum += pexp;
         s[i] = pexp;
       }
@@ -179,7 +182,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 
   // ---- epilogue: O / l -> bf16 -> out[b, q0 + tid, h, :]
-  if (q0 + tid < T) {
+  {
     const float inv = 1.f / l_run;
     __nv_bfloat16* og = Out + (((size_t)b * T + q0 + tid) * H + h) * D;
 #pragma unroll
@@ -226,7 +229,7 @@ static int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H
 
 cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, int B, int T, int H,
                                      float scale, cudaStream_t stream) {
-  if (B <= 0 || T <= 0 || H <= 0) { g_where = "bad sizes"; return cudaErrorInvalidValue; }
+  if (B <= 0 || T < attn::BM || H <= 0) { g_where = "bad sizes (T must be >= 128)"; return cudaErrorInvalidValue; }
   CUtensorMap tq, tk, tv;
   if (make_bthd_tmap(&tq, Q, B, T, H) || make_bthd_tmap(&tk, K, B, T, H) || make_bthd_tmap(&tv, V, B, T, H))
     return cudaErrorInvalidValue;

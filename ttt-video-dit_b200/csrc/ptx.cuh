@@ -67,10 +67,10 @@ static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar_addr, uint32_
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  // try_wait itself may sleep for a hardware-defined interval, so the clock is checked on every poll
   const long long t0 = clock64();
-  uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++n) & 0xFFF) == 0 && (clock64() - t0) > 6000000000LL) mbar_timeout_trap(smem_u32(bar), parity);
+    if ((clock64() - t0) > 4000000000LL) mbar_timeout_trap(smem_u32(bar), parity);
   }
 }
 

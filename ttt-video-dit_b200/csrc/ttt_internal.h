@@ -67,3 +67,10 @@ namespace tb {
 cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, int B, int T, int H,
                                      float scale, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo, const float* ln_w, const float* ln_b,
+                                  const uint8_t* img, const float* b1img, const float* b2img, uint8_t* qt, float* qb1,
+                                  float* qb2, void* dXQ, float* dlnw, float* dlnb, int BH, int H, int NC, int img_slots,
+                                  int G, int t0, int nsteps, cudaStream_t stream);
+}  // namespace tb

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bwd_common.cuh"
 #include "ptx.cuh"
 #include "ttt_internal.h"
 
@@ -50,6 +51,9 @@ struct BwdParams {
   const float *b1img, *b2img;     // [BH][img_slots][256], [BH][img_slots][64]
   float *dW1s, *dW2s, *db1s, *db2s;  // carried state gradient, fp32: [BH][256][64] x2, [BH][256], [BH][64]
   uint8_t* x2spill;                  // [BH][32 KB]
+  const uint8_t* qt;                 // Q-side factor tiles [BH][G] x 73728 B (ttt_mlp_bwd_q.cu)
+  const float *qb1, *qb2;            // Q-side b1/b2 contributions [BH][G][256], [BH][G][64]
+  int G;
   __nv_bfloat16 *dXQ, *dXK, *dXV, *dEta;  // outputs
   float *dlnw, *dlnb;                     // [BH][64], accumulated with atomics (pre-zeroed by the host wrapper)
   float *dW1, *db1, *dW2, *db2;           // final gradient w.r.t. the initial state (written when t_lo == 0)
@@ -59,154 +63,9 @@ struct BwdParams {
   unsigned* dbg;       // phase-timing buffer (debug builds)
 };
 
-__device__ __forceinline__ void gelu3(float z, float& g0, float& g1, float& g2) {
-  // gelu, gelu' (ops/utils.py:51-54) and gelu'' (ttt_backward/matching.py:47-55)
-  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
-  const float z2 = z * z;
-  const float a = fmaf(3.0f * c1, z2, c0);
-  const float t = tanh_fast(z * fmaf(c1, z2, c0));
-  const float s = fmaf(-t, t, 1.0f);
-  const float hz = 0.5f * z;
-  g0 = fmaf(hz, t, hz);
-  g1 = fmaf(hz * s, a, fmaf(0.5f, t, 0.5f));
-  g2 = s * (fmaf(2.0f, a, -c0) - z * t * a * a);
-}
-__device__ __forceinline__ float gelu1(float z, float& g1) {
-  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
-  const float z2 = z * z;
-  const float t = tanh_fast(z * fmaf(c1, z2, c0));
-  const float hz = 0.5f * z;
-  g1 = fmaf(hz * fmaf(-t, t, 1.0f), fmaf(3.0f * c1, z2, c0), fmaf(0.5f, t, 0.5f));
-  return fmaf(hz, t, hz);
-}
-
-// 32 fp32 -> bf16 -> 4 consecutive chunks of one SW128 row
-__device__ __forceinline__ void st_row32(uint32_t tile, int row, int chunk0, const float* v) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-    st_shared_v4(tile + sw128_off(row, chunk0 + c), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-}
-// read one 64-wide bf16 row of a SW128 tile into fp32
-__device__ __forceinline__ void ld_row64(uint32_t tile, int row, float* v) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t a, b, cc, d;
-    ld_shared_v4(tile + sw128_off(row, c), a, b, cc, d);
-    v[8 * c + 0] = bf16_lo(a); v[8 * c + 1] = bf16_hi(a); v[8 * c + 2] = bf16_lo(b); v[8 * c + 3] = bf16_hi(b);
-    v[8 * c + 4] = bf16_lo(cc); v[8 * c + 5] = bf16_hi(cc); v[8 * c + 6] = bf16_lo(d); v[8 * c + 7] = bf16_hi(d);
-  }
-}
-// column sums over the 32 lanes of a warp of a per-lane vector v[N] (N = 32 or 64) by recursive halving.
-// On return lane l holds in v[0] the sum of element l (N=32) or in v[0], v[1] the sums of elements l and l+32 (N=64).
-template <int N>
-__device__ __forceinline__ void warp_colsum(float* v, int lane) {
-  if (N == 64) {  // first fold 64 -> 32 pairs kept as (v[q], v[q+32]) handled by two independent 32-wide reductions
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      const bool up = (lane & m) != 0;
-#pragma unroll
-      for (int q = 0; q < m; ++q) {
-        float a0 = v[q], b0 = v[q + m], a1 = v[32 + q], b1 = v[32 + q + m];
-        float s0 = up ? a0 : b0, k0 = up ? b0 : a0, s1 = up ? a1 : b1, k1 = up ? b1 : a1;
-        v[q] = k0 + __shfl_xor_sync(0xffffffffu, s0, m);
-        v[32 + q] = k1 + __shfl_xor_sync(0xffffffffu, s1, m);
-      }
-    }
-    v[1] = v[32];
-  } else {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      const bool up = (lane & m) != 0;
-#pragma unroll
-      for (int q = 0; q < m; ++q) {
-        float a0 = v[q], b0 = v[q + m];
-        float s0 = up ? a0 : b0, k0 = up ? b0 : a0;
-        v[q] = k0 + __shfl_xor_sync(0xffffffffu, s0, m);
-      }
-    }
-  }
-}
-
-// column sums of a per-lane vector v[16] over the 32 lanes: afterwards v[0] = sum over lanes of element ((lane >> 1) & 15)
-__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
-#pragma unroll
-  for (int m = 8; m >= 1; m >>= 1) {
-    const bool up = (lane & (2 * m)) != 0;  // lane bits 4..1 select the element, bit 0 is folded last
-#pragma unroll
-    for (int q = 0; q < m; ++q) {
-      const float a0 = v[q], b0 = v[q + m];
-      const float snd = up ? a0 : b0, kp = up ? b0 : a0;
-      v[q] = kp + __shfl_xor_sync(0xffffffffu, snd, 2 * m);
-    }
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-// load 16 consecutive bf16 (two 16-B chunks c0, c0+1 of row r) from a SW128 tile
-__device__ __forceinline__ void ld_row16(uint32_t tile, int row, int chunk0, float* v) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t a, b, cc, d;
-    ld_shared_v4(tile + sw128_off(row, chunk0 + c), a, b, cc, d);
-    v[8 * c + 0] = bf16_lo(a); v[8 * c + 1] = bf16_hi(a); v[8 * c + 2] = bf16_lo(b); v[8 * c + 3] = bf16_hi(b);
-    v[8 * c + 4] = bf16_lo(cc); v[8 * c + 5] = bf16_hi(cc); v[8 * c + 6] = bf16_lo(d); v[8 * c + 7] = bf16_hi(d);
-  }
-}
-__device__ __forceinline__ void st_row16(uint32_t tile, int row, int chunk0, const float* v) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-    st_shared_v4(tile + sw128_off(row, chunk0 + c), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-}
-__device__ __forceinline__ void st_global16(__nv_bfloat16* g, const float* v) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-    *reinterpret_cast<uint4*>(g + 8 * c) = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                                      pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-}
-
-// ---- MMA issue helpers (single thread) -----------------------------------------------------------------------------
-// hidden-lane output: D[h] (128 lanes x N cols) = A_tile[h] (K-major, [256][64]) . B  ; 4 k-steps
-__device__ __forceinline__ void mma_hid(uint32_t d0, uint32_t d1, uint32_t a_tile, uint32_t b_tile, bool b_mn, int n,
-                                        bool acc) {
-  const uint32_t idesc = make_idesc_bf16(128, n, false, b_mn);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const uint64_t da = make_desc_sw128(a_tile + h * 16384, 16, 1024);
-    const uint64_t db = b_mn ? make_desc_sw128(b_tile, 1024, 1024) : make_desc_sw128(b_tile, 16, 1024);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_ss(h ? d1 : d0, desc_advance(da, 32 * k), desc_advance(db, b_mn ? 2048 * k : 32 * k), idesc, acc || k > 0);
-  }
-}
-// token-lane output: D = A_tile (hidden-lane tile viewed MN-major, [256 j][64 tok]) . B_tile ([256 j][64 f], MN-major);
-// 16 k-steps over the hidden dim.  LBO = 0 makes the second 64-row block of A alias the first, so rows 64-127 of D are a
-// copy of rows 0-63: every token row is then readable from two TMEM lane halves and all 8 warps share the token phases
-// (thread <-> (row, 16-column quarter)); pinned by umma self-test mode 6.
-__device__ __forceinline__ void mma_tok(uint32_t d, uint32_t a_tile, uint32_t b_tile, bool acc) {
-  const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
-  const uint64_t da = make_desc_sw128(a_tile, 0, 1024);
-  const uint64_t db = make_desc_sw128(b_tile, 1024, 1024);
-#pragma unroll
-  for (int k = 0; k < 16; ++k) umma_ss(d, desc_advance(da, 2048 * k), desc_advance(db, 2048 * k), idesc, acc || k > 0);
-}
-
-#define MMA_WAIT()                 \
-  do {                             \
-    mbar_wait(mma_bar, mma_phase); \
-    mma_phase ^= 1;                \
-    tc_fence_after();              \
-  } while (0)
-#define PHASE_SYNC()     \
-  do {                   \
-    fence_proxy_async(); \
-    tc_fence_before();   \
-    __syncthreads();     \
-  } while (0)
-
 __global__ void __launch_bounds__(NT, 1)
 ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
+                   const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -244,7 +103,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (tid == 0) {
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
   if (warp == 0) tmem_alloc<512>(tmem_ptr);
   if (tid < 64) {
@@ -281,6 +140,17 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
   uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0;
 
+  const uint8_t* qt_bh = p.qt + (size_t)bh * p.G * 73728;
+  // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t (Xbar2^T -> slot xs, dZbar1^T -> slot zs,
+  // dZbar2 -> TT0).  Thread 0 only.
+  auto load_q_contrib = [&](int t, uint32_t xs, uint32_t zs) {
+    const uint8_t* src = qt_bh + (size_t)(t - p.t0) * 73728;
+    mbar_expect_tx(bar_qd, 8192 + 73728);
+    tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)t * CS), bar_qd);
+    bulk_load_1d(smem + xs, src, 32768, bar_qd);
+    bulk_load_1d(smem + zs, src + 32768, 32768, bar_qd);
+    bulk_load_1d(smem + SM_TT0, src + 65536, 8192, bar_qd);
+  };
   // first iteration's loads
   if (tid == 0) {
     const int t = p.t_hi;
@@ -289,16 +159,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bulk_load_1d(smem + sW1, im, 32768, bar_w1);
     mbar_expect_tx(bar_w2, 32768);
     bulk_load_1d(smem + SM_W2I, im + 32768, 32768, bar_w2);
-    if (t < p.NC) {
-      mbar_expect_tx(bar_kv, 16384);
-      tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
-      tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
-    }
-    if (t > 0) {
-      mbar_expect_tx(bar_qd, 16384);
-      tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)(t - 1) * CS), bar_qd);
-      tma_load_2d(smem + SM_TDO, &tmDO, 0, (int)(row_bh + (size_t)(t - 1) * CS), bar_qd);
-    }
+    mbar_expect_tx(bar_kv, 16384);
+    tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
+    tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
+    load_q_contrib(t, sA, sB);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -308,35 +172,52 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
   float nb1 = p.b1img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * HID + j], nb2 = 0.f;
+  float nq1 = p.qb1[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * HID + j], nq2 = 0.f;
   unsigned short neta = 0;
   if (tid < 64) {
     nb2 = p.b2img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * F + tid];
+    nq2 = p.qb2[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * F + tid];
     if (p.t_hi < p.NC) neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)p.t_hi * CS + tid];
   }
   for (int t = p.t_hi; t >= p.t_lo; --t) {
-    const bool has_k = t < p.NC, has_q = t > 0;
+    const bool has_k = true;
     const size_t slot = (size_t)(t - p.t0);
     // per-iteration small vectors were prefetched into registers during the previous iteration (nb1/nb2/neta)
     const float b1t = nb1;
+    const float q1t = nq1;
     if (tid < 64) {
       b2t[tid] = nb2;
-      if (has_k) etas[tid] = __uint_as_float((uint32_t)neta << 16);
+      etas[tid] = __uint_as_float((uint32_t)neta << 16);
       etasum[tid] = 0.f;
+      db2c[tid] += nq2;  // Q-side contribution of step t to d b2 (state after step t)
     }
-    if (t > p.t_lo) {  // prefetch for iteration t-1 (always a K iteration)
+    db1r += q1t;         // ... and to d b1
+    if (t > p.t_lo) {  // prefetch for iteration t-1
       const size_t ns = slot - 1;
       nb1 = p.b1img[((size_t)bh * p.img_slots + ns) * HID + j];
+      nq1 = p.qb1[((size_t)bh * p.G + ns) * HID + j];
       if (tid < 64) {
         nb2 = p.b2img[((size_t)bh * p.img_slots + ns) * F + tid];
+        nq2 = p.qb2[((size_t)bh * p.G + ns) * F + tid];
         neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)(t - 1) * CS + tid];
       }
     }
     mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1;
     mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1;
-    if (has_k) { mbar_wait(bar_kv, ph_kv); ph_kv ^= 1; }
-    if (has_q) { mbar_wait(bar_qd, ph_qd); ph_qd ^= 1; }
+    mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+    mbar_wait(bar_qd, ph_qd); ph_qd ^= 1;
     __syncthreads();  // b2t / etas visible
       TICK(0);
+
+    // ===== apply the Q-side contribution of step t to the carried gradient (outer products of the factor tiles written
+    //       by ttt_mlp_bwd_q_kernel):  dW2 += Xbar2^T dZbar2 ;  dW1^T += dZbar1^T Q
+    if (tid == 0) {
+      tc_fence_after();
+      mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sA, sbase + SM_TT0, true, 64, true);
+      mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TQ, true, 64, true);
+      tc_commit(mma_bar);
+    }
+    MMA_WAIT();
 
     if (has_k) {
       // ===== A0 [H]: bf16 copies of the carried gradient accumulators: CW1 -> sA, CW2 -> sB
@@ -650,172 +531,21 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncthreads();
       TICK(13);
-    } else {
-      // Q-only iteration (t == NC): the W1 image sits in sW1; the Q chain below expects it in sA
-      const uint32_t tmp = sA; sA = sW1; sW1 = tmp;
     }
 
-    // next iteration's K/V tiles and W1 image (their buffers are free now)
+    // next iteration's loads (every buffer they target was last used by the A11 batch, which has completed):
+    //   K/V tiles, W1 image -> sC, W2 image, Q tile + Q-side factor tiles (Xbar2^T -> sW1, dZbar1^T -> sA, dZbar2 -> TT0)
     const bool more = t > p.t_lo;
     if (tid == 0 && more) {
-      const int tn = t - 1;  // always < NC
+      const int tn = t - 1;
       mbar_expect_tx(bar_kv, 16384);
       tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);
       tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);
       mbar_expect_tx(bar_w1, 32768);
       bulk_load_1d(smem + sC, img_bh + (size_t)(tn - p.t0) * 65536, 32768, bar_w1);
-    }
-
-    if (has_q) {
-      // ===== Q1 MMA: Zbar1^T = W1 . Q^T -> (S1,S2)
-      if (tid == 0) {
-        tc_fence_after();
-        mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + sA, sbase + SM_TQ, false, 64, false);
-        tc_commit(mma_bar);
-      }
-      MMA_WAIT();
-      TICK(14);
-      // ===== Q2 [H]: X2bar -> sB, gelu'(Zbar1)
-      {
-        const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a0, a1;
-            v[i] = gelu1(v[i] + b1t, a0);
-            v[i + 1] = gelu1(v[i + 1] + b1t, a1);
-            g1p[16 * c + i / 2] = pack_bf16(a0, a1);
-          }
-          st_row32(sbase + sB, j, 4 * c, v);
-        }
-      }
-      PHASE_SYNC();
-      TICK(15);
-      // ===== Q3 MMA: Zbar2 = X2bar . W2 -> S3
-      if (tid == 0) {
-        tc_fence_after();
-        mma_tok(tmem + TM_S3, sbase + sB, sbase + SM_W2I, false);
-        tc_commit(mma_bar);
-      }
-      MMA_WAIT();
-      TICK(16);
-      // ===== Q4 [T] (all warps): output LN backward: dZbar2 -> TT0 ; d gamma, d beta, d b2 column sums
-      {
-        float z[16], d[16];
-        tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(z));
-        ld_row16(sbase + SM_TDO, trow, 2 * cq, d);
-        tc_wait_ld();
-        float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int f = 0; f < 16; ++f) { z[f] += b2t[c0 + f]; a1 += z[f]; a2 = fmaf(z[f], z[f], a2); }
-        xB[cq * 64 + trow] = make_float2(a1, a2);
-        __syncthreads();
-        a1 = 0.f; a2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 v = xB[q * 64 + trow]; a1 += v.x; a2 += v.y; }
-        const float mu = a1 * (1.f / 64.f);
-        const float rstd = rsqrtf(fmaxf(a2 * (1.f / 64.f) - mu * mu, 0.f) + 1e-8f);
-        float s1 = 0.f, s2 = 0.f;
-        float cg[16];
-#pragma unroll
-        for (int f = 0; f < 16; ++f) {
-          z[f] = (z[f] - mu) * rstd;
-          cg[f] = d[f] * z[f];               // d gamma contribution
-          const float dxh = d[f] * lnw[c0 + f];
-          s1 += dxh;
-          s2 = fmaf(dxh, z[f], s2);
-        }
-        xA[cq * 64 + trow] = make_float4(s1, s2, 0.f, 0.f);
-        __syncthreads();
-        s1 = 0.f; s2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float4 v = xA[q * 64 + trow]; s1 += v.x; s2 += v.y; }
-#pragma unroll
-        for (int f = 0; f < 16; ++f)
-          z[f] = (fmaf(64.f, d[f] * lnw[c0 + f], -s1) - z[f] * s2) * (rstd * (1.f / 64.f));  // dZbar2
-        st_row16(sbase + SM_TT0, trow, 2 * cq, z);
-        warp_colsum16(z, lane);
-        warp_colsum16(cg, lane);
-        warp_colsum16(d, lane);
-        if ((lane & 1) == 0) {
-          const int f = c0 + (lane >> 1);
-          atomicAdd(&db2c[f], z[0]);
-          atomicAdd(&dgam[f], cg[0]);
-          atomicAdd(&dbet[f], d[0]);
-        }
-      }
-      PHASE_SYNC();
-      TICK(17);
-      // ===== Q5 MMA: dX2bar^T = W2 . dZbar2^T -> (S1,S2) ; dW2 += X2bar^T dZbar2
-      if (tid == 0) {
-        tc_fence_after();
-        mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + SM_W2I, sbase + SM_TT0, false, 64, false);
-        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sB, sbase + SM_TT0, true, 64, true);
-        tc_commit(mma_bar);
-      }
-      MMA_WAIT();
-      TICK(18);
-      if (tid == 0 && more) {  // W2 image buffer is free: fetch the next one
-        mbar_expect_tx(bar_w2, 32768);
-        bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
-      }
-      // ===== Q6 [H]: dZbar1 = dX2bar * gelu'(Zbar1) -> sW1 ; d b1 += sum
-      {
-        const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint32_t gp1 = g1p[16 * c + i / 2];
-            v[i] *= bf16_lo(gp1);
-            v[i + 1] *= bf16_hi(gp1);
-            acc += v[i] + v[i + 1];
-          }
-          st_row32(sbase + sW1, j, 4 * c, v);
-        }
-        db1r += acc;
-      }
-      PHASE_SYNC();
-      TICK(19);
-      // ===== Q7 MMA: dW1^T += dZbar1^T Q ; dQ_u = dZbar1 . W1 -> S3
-      if (tid == 0) {
-        tc_fence_after();
-        mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sW1, sbase + SM_TQ, true, 64, true);
-        mma_tok(tmem + TM_S3, sbase + sW1, sbase + sA, false);
-        tc_commit(mma_bar);
-      }
-      MMA_WAIT();
-      TICK(20);
-      // ===== Q8 [T]: dQ = dO + dQ_u
-      {
-        float a[16], d[16];
-        tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(a));
-        ld_row16(sbase + SM_TDO, trow, 2 * cq, d);
-        tc_wait_ld();
-#pragma unroll
-        for (int f = 0; f < 16; ++f) a[f] += d[f];
-        st_global16(p.dXQ + (row_bh + (size_t)(t - 1) * CS + trow) * F + c0, a);
-      }
-      tc_fence_before();
-      __syncthreads();
-      TICK(21);
-    } else if (tid == 0 && more) {  // (cannot happen: t == 0 is always the last iteration) keep the W2 prefetch paired
       mbar_expect_tx(bar_w2, 32768);
-      bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
-    }
-    // next iteration's Q / dO tiles
-    if (tid == 0 && more && (t - 1) > 0) {
-      mbar_expect_tx(bar_qd, 16384);
-      tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)(t - 2) * CS), bar_qd);
-      tma_load_2d(smem + SM_TDO, &tmDO, 0, (int)(row_bh + (size_t)(t - 2) * CS), bar_qd);
+      bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(tn - p.t0) * 65536 + 32768, 32768, bar_w2);
+      load_q_contrib(tn, sW1, sA);
     }
     // rotate slot roles: the next W1 image was fetched into sC
     {
@@ -864,7 +594,9 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------------------ host
 size_t mlp_backward_workspace_bytes(int B, int H, int G) {
   const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
-  return bh * (2 * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + 2 * 65536 + 1024 + 256 + 32768) + 1024;
+  const size_t g = (size_t)G;
+  return bh * (2 * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + 2 * (g * 73728 + g * 1024 + g * 256) + 2 * 65536 +
+               1024 + 256 + 32768) + 1024;
 }
 
 cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
@@ -889,6 +621,10 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   b2img[1] = reinterpret_cast<float*>(w); w += bh * slots * 256;
   float* db1s = reinterpret_cast<float*>(w); w += bh * 1024;
   float* db2s = reinterpret_cast<float*>(w); w += bh * 256;
+  uint8_t* qt[2]; float *qb1[2], *qb2[2];          // Q-side factor tiles / vectors of a group (ping-pong like the images)
+  for (int i = 0; i < 2; ++i) { qt[i] = w; w += bh * (size_t)G * 73728; }
+  for (int i = 0; i < 2; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 1024; }
+  for (int i = 0; i < 2; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 256; }
 
   CUtensorMap tq, tk, tv, tdo;
   const uint64_t rows = (uint64_t)bh * NC * 64;
@@ -918,13 +654,15 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     }
   }
   const int K = (NC + G - 1) / G;
-  auto traj = [&](int g) -> cudaError_t {  // images of W_{t0} .. W_{t1-1} (and W_NC for the last group) into buffer g&1
+  // side stream, per group g: trajectory (images of W_{t0} .. W_{t1}) then the Q-side kernel (steps t0 .. t1-1)
+  auto traj = [&](int g) -> cudaError_t {
     const int t0 = g * G;
     const int t1 = (t0 + G < NC) ? t0 + G : NC;
-    const bool last = (g == K - 1);
-    cudaError_t e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0,
-                                          last ? (t1 - t0) : (t1 - t0 - 1), img[g & 1], b1img[g & 1], b2img[g & 1],
-                                          (int)slots, sd.s);
+    cudaError_t e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0, t1 - t0,
+                                          img[g & 1], b1img[g & 1], b2img[g & 1], (int)slots, sd.s);
+    if (e != cudaSuccess) return e;
+    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[g & 1], b1img[g & 1], b2img[g & 1], qt[g & 1], qb1[g & 1],
+                              qb2[g & 1], dXQ, dlnw, dlnb, (int)bh, H, NC, (int)slots, G, t0, t1 - t0, sd.s);
     if (e != cudaSuccess) return e;
     return cudaEventRecord(sd.evT[g & 1], sd.s);
   };
@@ -943,16 +681,17 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.img = img[g & 1]; p.b1img = b1img[g & 1]; p.b2img = b2img[g & 1];
     p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
     p.x2spill = x2s;
+    p.qt = qt[g & 1]; p.qb1 = qb1[g & 1]; p.qb2 = qb2[g & 1]; p.G = G;
     p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
     p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = reinterpret_cast<__nv_bfloat16*>(dEta);
     p.dlnw = dlnw; p.dlnb = dlnb;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
     p.H = H; p.NC = NC; p.img_slots = (int)slots;
-    p.t_hi = last ? NC : t1 - 1;
+    p.t_hi = t1 - 1;
     p.t_lo = t0; p.t0 = t0;
     p.first = last ? 1 : 0;
     p.dbg = (g == 0) ? g_timing_buf : nullptr;  // time the last launch (a full group)
-    bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, tdo, p);
+    bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
     if (g >= 2) {  // buffer g&1 is free again once this reverse launch is done: recompute group g-2 into it
       TB_TRY(cudaEventRecord(sd.evR[g & 1], stream), "record reverse");

@@ -63,8 +63,8 @@ _last_groups = [1]
 
 
 def launches_bwd():
-    """2 memsets are library calls; our kernels: one trajectory + one reverse launch per checkpoint group."""
-    return 2 * _last_groups[0]
+    """2 memsets are library calls; our kernels per checkpoint group: trajectory + Q-side kernel + sequential K-side kernel."""
+    return 3 * _last_groups[0]
 
 
 _ws_cache = {}
