@@ -90,7 +90,9 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_w1r = bars + 4;   // W1 image reload (for dK / dQ GEMMs)
   uint64_t* bar_w2 = bars + 5;    // W2 image
   uint64_t* bar_x2 = bars + 6;    // X2 tile reload
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_aux = bars + 7;   // completion of the early dW2 accumulations (frees two tile slots)
+  uint64_t* bar_xb = bars + 8;    // Q-side Xbar2^T factor tile
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
   float4* xA = reinterpret_cast<float4*>(smem + SM_XB);          // [4][64]
   float2* xB = reinterpret_cast<float2*>(smem + SM_XB + 4096);   // [4][64]
   float* epart = reinterpret_cast<float*>(smem + SM_XB + 6144);  // [4][64]
@@ -101,7 +103,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int c0 = 16 * cq;
 
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
@@ -138,16 +140,18 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
   uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
-  uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0;
+  uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0, ph_aux = 0, ph_xb = 0;
 
   const uint8_t* qt_bh = p.qt + (size_t)bh * p.G * 73728;
-  // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t (Xbar2^T -> slot xs, dZbar1^T -> slot zs,
-  // dZbar2 -> TT0).  Thread 0 only.
-  auto load_q_contrib = [&](int t, uint32_t xs, uint32_t zs) {
+  // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t.  Thread 0 only.
+  auto load_xb = [&](int t, uint32_t xs) {  // Xbar2^T factor tile of step t
+    mbar_expect_tx(bar_xb, 32768);
+    bulk_load_1d(smem + xs, qt_bh + (size_t)(t - p.t0) * 73728, 32768, bar_xb);
+  };
+  auto load_q_rest = [&](int t, uint32_t zs) {  // Q_t tile, dZbar1^T -> slot zs, dZbar2 -> TT0
     const uint8_t* src = qt_bh + (size_t)(t - p.t0) * 73728;
-    mbar_expect_tx(bar_qd, 8192 + 73728);
+    mbar_expect_tx(bar_qd, 8192 + 32768 + 8192);
     tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)t * CS), bar_qd);
-    bulk_load_1d(smem + xs, src, 32768, bar_qd);
     bulk_load_1d(smem + zs, src + 32768, 32768, bar_qd);
     bulk_load_1d(smem + SM_TT0, src + 65536, 8192, bar_qd);
   };
@@ -162,7 +166,8 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_expect_tx(bar_kv, 16384);
     tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
     tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
-    load_q_contrib(t, sA, sB);
+    load_xb(t, sA);
+    load_q_rest(t, sB);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -206,6 +211,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1;
     mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
     mbar_wait(bar_qd, ph_qd); ph_qd ^= 1;
+    mbar_wait(bar_xb, ph_xb); ph_xb ^= 1;
     __syncthreads();  // b2t / etas visible
       TICK(0);
 
@@ -477,15 +483,25 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       PHASE_SYNC();
       TICK(9);
-      // ===== A9 MMA: dX2^T = W2 . dZ2^T + CW2 . (-eta gradZ2)^T -> (S1,S2)
+      // ===== A9 MMA: dX2^T = W2 . dZ2^T + CW2 . (-eta gradZ2)^T -> (S1,S2)   (waited)
+      //       then, not waited here: dW2 += DG1^T gradZ2 + X2^T dZ2 -- their completion (bar_aux) frees the DG1 and X2
+      //       slots early so that next iteration's tiles stream in under A10/A11
+      mbar_wait(bar_x2, ph_x2); ph_x2 ^= 1;
       if (tid == 0) {
         tc_fence_after();
         mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + SM_W2I, sbase + SM_TT0, false, 64, false);
         mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + sB, sbase + SM_TT2, false, 64, true);
         tc_commit(mma_bar);
+        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sW1, sbase + SM_TT1, true, 64, true);
+        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sC, sbase + SM_TT0, true, 64, true);
+        tc_commit(bar_aux);
       }
       MMA_WAIT();
       TICK(10);
+      if (tid == 0 && t > p.t_lo) {  // the W2 image buffer is free now: fetch the next one
+        mbar_expect_tx(bar_w2, 32768);
+        bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
+      }
       // ===== A10 [H]: dZ1 = dX2 * gelu'(Z1) + term2 -> sB ; d b1 += sum dZ1
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
@@ -507,15 +523,18 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         db1r += acc;
       }
       mbar_wait(bar_w1r, ph_w1r); ph_w1r ^= 1;
-      mbar_wait(bar_x2, ph_x2); ph_x2 ^= 1;
+      mbar_wait(bar_aux, ph_aux); ph_aux ^= 1;   // DG1 (sW1) and X2 (sC) are no longer read by any MMA
+      if (tid == 0 && t > p.t_lo) {
+        mbar_expect_tx(bar_w1, 32768);
+        bulk_load_1d(smem + sC, img_bh + (size_t)(t - 1 - p.t0) * 65536, 32768, bar_w1);
+        load_xb(t - 1, sW1);
+      }
       PHASE_SYNC();
       TICK(11);
-      // ===== A11 MMA: dK: S0 += dZ1 . W1 ; dW2 += DG1^T gradZ2 + X2^T dZ2 ; dW1^T += dZ1^T K
+      // ===== A11 MMA: dK: S0 += dZ1 . W1 ; dW1^T += dZ1^T K
       if (tid == 0) {
         tc_fence_after();
         mma_tok(tmem + TM_S0, sbase + sB, sbase + sA, true);
-        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sW1, sbase + SM_TT1, true, 64, true);
-        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sC, sbase + SM_TT0, true, 64, true);
         mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TK, true, 64, true);
         tc_commit(mma_bar);
       }
@@ -533,19 +552,14 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       TICK(13);
     }
 
-    // next iteration's loads (every buffer they target was last used by the A11 batch, which has completed):
-    //   K/V tiles, W1 image -> sC, W2 image, Q tile + Q-side factor tiles (Xbar2^T -> sW1, dZbar1^T -> sA, dZbar2 -> TT0)
+    // next iteration's remaining loads (buffers last used by the A11 batch): K/V tiles, Q tile, dZbar1^T -> sA, dZbar2 -> TT0
     const bool more = t > p.t_lo;
     if (tid == 0 && more) {
       const int tn = t - 1;
       mbar_expect_tx(bar_kv, 16384);
       tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);
       tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);
-      mbar_expect_tx(bar_w1, 32768);
-      bulk_load_1d(smem + sC, img_bh + (size_t)(tn - p.t0) * 65536, 32768, bar_w1);
-      mbar_expect_tx(bar_w2, 32768);
-      bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(tn - p.t0) * 65536 + 32768, 32768, bar_w2);
-      load_q_contrib(tn, sW1, sA);
+      load_q_rest(tn, sA);
     }
     // rotate slot roles: the next W1 image was fetched into sC
     {
@@ -592,11 +606,15 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }  // namespace bwd
 
 // ------------------------------------------------------------------------------------------------ host
+// Recompute state is kept in a ring of kRing group buffers so that the trajectory / Q-side kernels of later groups run
+// ahead of the sequential K-side kernel (three streams).
+constexpr int kRing = 3;
+
 size_t mlp_backward_workspace_bytes(int B, int H, int G) {
   const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
   const size_t g = (size_t)G;
-  return bh * (2 * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + 2 * (g * 73728 + g * 1024 + g * 256) + 2 * 65536 +
-               1024 + 256 + 32768) + 1024;
+  return bh * (kRing * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + kRing * (g * 73728 + g * 1024 + g * 256) +
+               2 * 65536 + 1024 + 256 + 32768) + 1024;
 }
 
 cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
@@ -609,22 +627,19 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   w = reinterpret_cast<uint8_t*>(((uintptr_t)w + 1023) & ~(uintptr_t)1023);
-  uint8_t* img[2]; float *b1img[2], *b2img[2];   // ping-pong: trajectory(g-1) overlaps reverse(g) on a side stream
-  img[0] = w;                            w += bh * slots * 65536;
-  img[1] = w;                            w += bh * slots * 65536;
+  uint8_t* img[kRing]; float *b1img[kRing], *b2img[kRing];
+  for (int i = 0; i < kRing; ++i) { img[i] = w; w += bh * slots * 65536; }
   uint8_t* x2s = w;                      w += bh * 32768;
   float* dW1s = reinterpret_cast<float*>(w); w += bh * 65536;
   float* dW2s = reinterpret_cast<float*>(w); w += bh * 65536;
-  b1img[0] = reinterpret_cast<float*>(w); w += bh * slots * 1024;
-  b1img[1] = reinterpret_cast<float*>(w); w += bh * slots * 1024;
-  b2img[0] = reinterpret_cast<float*>(w); w += bh * slots * 256;
-  b2img[1] = reinterpret_cast<float*>(w); w += bh * slots * 256;
+  for (int i = 0; i < kRing; ++i) { b1img[i] = reinterpret_cast<float*>(w); w += bh * slots * 1024; }
+  for (int i = 0; i < kRing; ++i) { b2img[i] = reinterpret_cast<float*>(w); w += bh * slots * 256; }
   float* db1s = reinterpret_cast<float*>(w); w += bh * 1024;
   float* db2s = reinterpret_cast<float*>(w); w += bh * 256;
-  uint8_t* qt[2]; float *qb1[2], *qb2[2];          // Q-side factor tiles / vectors of a group (ping-pong like the images)
-  for (int i = 0; i < 2; ++i) { qt[i] = w; w += bh * (size_t)G * 73728; }
-  for (int i = 0; i < 2; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 1024; }
-  for (int i = 0; i < 2; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 256; }
+  uint8_t* qt[kRing]; float *qb1[kRing], *qb2[kRing];   // Q-side factor tiles / vectors of a group
+  for (int i = 0; i < kRing; ++i) { qt[i] = w; w += bh * (size_t)G * 73728; }
+  for (int i = 0; i < kRing; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 1024; }
+  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 256; }
 
   CUtensorMap tq, tk, tv, tdo;
   const uint64_t rows = (uint64_t)bh * NC * 64;
@@ -639,49 +654,59 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   TB_TRY(cudaMemsetAsync(dlnw, 0, bh * 64 * sizeof(float), stream), "memset dlnw");
   TB_TRY(cudaMemsetAsync(dlnb, 0, bh * 64 * sizeof(float), stream), "memset dlnb");
 
-  // side stream + events (one set per device, created once)
-  struct Side { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, evT[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr}; };
+  // three streams per device (created once): T = trajectory, Q = Q-side kernel, main = sequential K-side kernel
+  struct Side {
+    cudaStream_t sT = nullptr, sQ = nullptr;
+    cudaEvent_t fork = nullptr, evT[kRing] = {}, evQ[kRing] = {}, evR[kRing] = {};
+  };
   static Side sides[64];
   int dev = 0;
   TB_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   Side& sd = sides[dev & 63];
-  if (!sd.s) {
-    TB_TRY(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking), "side stream");
+  if (!sd.sT) {
+    TB_TRY(cudaStreamCreateWithFlags(&sd.sT, cudaStreamNonBlocking), "side stream");
+    TB_TRY(cudaStreamCreateWithFlags(&sd.sQ, cudaStreamNonBlocking), "side stream");
     TB_TRY(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming), "event");
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kRing; ++i) {
       TB_TRY(cudaEventCreateWithFlags(&sd.evT[i], cudaEventDisableTiming), "event");
+      TB_TRY(cudaEventCreateWithFlags(&sd.evQ[i], cudaEventDisableTiming), "event");
       TB_TRY(cudaEventCreateWithFlags(&sd.evR[i], cudaEventDisableTiming), "event");
     }
   }
   const int K = (NC + G - 1) / G;
-  // side stream, per group g: trajectory (images of W_{t0} .. W_{t1}) then the Q-side kernel (steps t0 .. t1-1)
-  auto traj = [&](int g) -> cudaError_t {
+  // group g -> ring buffer r = g % kRing: trajectory (images of W_{t0} .. W_{t1}) on stream T, then the Q-side kernel
+  // (steps t0 .. t1-1) on stream Q
+  auto recompute = [&](int g) -> cudaError_t {
+    const int r = g % kRing;
     const int t0 = g * G;
     const int t1 = (t0 + G < NC) ? t0 + G : NC;
     cudaError_t e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0, t1 - t0,
-                                          img[g & 1], b1img[g & 1], b2img[g & 1], (int)slots, sd.s);
+                                          img[r], b1img[r], b2img[r], (int)slots, sd.sT);
     if (e != cudaSuccess) return e;
-    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[g & 1], b1img[g & 1], b2img[g & 1], qt[g & 1], qb1[g & 1],
-                              qb2[g & 1], dXQ, dlnw, dlnb, (int)bh, H, NC, (int)slots, G, t0, t1 - t0, sd.s);
+    if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;
+    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[r], b1img[r], b2img[r], qt[r], qb1[r], qb2[r], dXQ, dlnw, dlnb,
+                              (int)bh, H, NC, (int)slots, G, t0, t1 - t0, sd.sQ);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(sd.evT[g & 1], sd.s);
+    return cudaEventRecord(sd.evQ[r], sd.sQ);
   };
   TB_TRY(cudaEventRecord(sd.fork, stream), "fork record");
-  TB_TRY(cudaStreamWaitEvent(sd.s, sd.fork, 0), "fork wait");
-  TB_TRY(traj(K - 1), "trajectory launch");
-  if (K > 1) TB_TRY(traj(K - 2), "trajectory launch");
+  TB_TRY(cudaStreamWaitEvent(sd.sT, sd.fork, 0), "fork wait");
+  TB_TRY(cudaStreamWaitEvent(sd.sQ, sd.fork, 0), "fork wait");
+  for (int i = 0; i < kRing && K - 1 - i >= 0; ++i) TB_TRY(recompute(K - 1 - i), "trajectory / Q launch");
   for (int g = K - 1; g >= 0; --g) {
+    const int r = g % kRing;
     const int t0 = g * G;
     const int t1 = (t0 + G < NC) ? t0 + G : NC;
     const bool last = (g == K - 1);
-    TB_TRY(cudaStreamWaitEvent(stream, sd.evT[g & 1], 0), "wait trajectory");
+    TB_TRY(cudaStreamWaitEvent(stream, sd.evQ[r], 0), "wait Q-side");
     bwd::BwdParams p{};
     p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
     p.ln_w = ln_w; p.ln_b = ln_b;
-    p.img = img[g & 1]; p.b1img = b1img[g & 1]; p.b2img = b2img[g & 1];
+    p.img = img[r]; p.b1img = b1img[r]; p.b2img = b2img[r];
     p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
     p.x2spill = x2s;
-    p.qt = qt[g & 1]; p.qb1 = qb1[g & 1]; p.qb2 = qb2[g & 1]; p.G = G;
+    p.qt = qt[r]; p.qb1 = qb1[r]; p.qb2 = qb2[r]; p.G = G;
     p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
     p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = reinterpret_cast<__nv_bfloat16*>(dEta);
     p.dlnw = dlnw; p.dlnb = dlnb;
@@ -693,10 +718,10 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.dbg = (g == 0) ? g_timing_buf : nullptr;  // time the last launch (a full group)
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
-    if (g >= 2) {  // buffer g&1 is free again once this reverse launch is done: recompute group g-2 into it
-      TB_TRY(cudaEventRecord(sd.evR[g & 1], stream), "record reverse");
-      TB_TRY(cudaStreamWaitEvent(sd.s, sd.evR[g & 1], 0), "wait reverse");
-      TB_TRY(traj(g - 2), "trajectory launch");
+    if (g >= kRing) {  // ring buffer r is free again once this launch is done: recompute group g - kRing into it
+      TB_TRY(cudaEventRecord(sd.evR[r], stream), "record reverse");
+      TB_TRY(cudaStreamWaitEvent(sd.sT, sd.evR[r], 0), "wait reverse");
+      TB_TRY(recompute(g - kRing), "trajectory / Q launch");
     }
   }
   return cudaSuccess;
