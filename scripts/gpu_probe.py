@@ -76,6 +76,36 @@ for rep in range(2):
             print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn)}, flush=True)
     buf.zero_()
 """ % (ROOT, ROOT, ROOT),
+    "timeline": """
+import torch, sys, json
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from ttt_video_dit_b200 import mlp_tk
+from torch.profiler import profile, ProfilerActivity
+B,H,NC,G = 1,48,282,16
+g = torch.Generator().manual_seed(0)
+rn = lambda *s: torch.randn(*s, generator=g)
+bf = lambda t: t.to(torch.bfloat16).cuda()
+q = bf(torch.nn.functional.normalize(rn(B,H,NC,64,64), dim=-1)).requires_grad_(True)
+k = bf(torch.nn.functional.normalize(rn(B,H,NC,64,64), dim=-1)).requires_grad_(True)
+v = bf(rn(B,H,NC,64,64)).requires_grad_(True)
+e = bf((0.1/64)*torch.sigmoid(rn(B,H,NC,64))/64).requires_grad_(True)
+go = bf(rn(B,H,NC,64,64))
+prm = [t.cuda().requires_grad_(True) for t in (1+0.1*rn(H,64), 0.1*rn(H,64), (0.02*rn(H,64,256)).unsqueeze(0).repeat(B,1,1,1), torch.zeros(B,H,1,256), (0.02*rn(H,256,64)).unsqueeze(0).repeat(B,1,1,1), torch.zeros(B,H,1,64))]
+for _ in range(2):
+    out = mlp_tk.ttt_mlp_op(*prm, q, v, k, e, G); out.backward(go)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    out = mlp_tk.ttt_mlp_op(*prm, q, v, k, e, G); out.backward(go)
+    torch.cuda.synchronize()
+evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and 'ttt' in ev.name]
+evs.sort(key=lambda ev: ev.time_range.start)
+t0 = evs[0].time_range.start
+for ev in evs[:70]:
+    nm = 'FWD ' if 'fwd_kernelILb0' in ev.name else ('TRAJ' if 'fwd_kernelILb1' in ev.name else ('Q   ' if 'bwd_q' in ev.name else 'K   '))
+    print(nm, 'start %%8.1f us  dur %%7.1f us' %% ((ev.time_range.start - t0), ev.time_range.end - ev.time_range.start), flush=True)
+print('total span us', evs[-1].time_range.end - t0)
+""" % (ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

@@ -22,13 +22,15 @@ namespace tb {
 namespace lin {
 
 constexpr int CS = 16, F = 64, NT = 128;
-constexpr int ZP = 65;  // padded fp32 row of the transpose buffer
+constexpr int ZP = 66;  // fp32 transpose buffer row: two 32-column halves padded to 33 (bank-conflict free for the
+                        // (row, half) thread pairs of the LayerNorm phase)
+__device__ __forceinline__ int zidx(int row, int f) { return row * ZP + (f >> 5) * 33 + (f & 31); }
 
 constexpr uint32_t SM_W1B = 0;                       // [128][64] bf16 K-major                   16 KB
 constexpr uint32_t SM_TOK = 16384;                   // 2 slots x 64 rows: K_s0,K_s1,Q_s0,Q_s1   16 KB
 constexpr uint32_t SM_V = SM_TOK + 16384;            // 2 slots x 32 rows: V_s0, V_s1             8 KB
 constexpr uint32_t SM_GT = SM_V + 8192;              // G^T operand: 2 blocks x 32 token rows     8 KB
-constexpr uint32_t SM_ZT = SM_GT + 8192;             // fp32 [64 token threads][65]              16640 B
+constexpr uint32_t SM_ZT = SM_GT + 8192;             // fp32 [64 token rows][66]                 16896 B
 constexpr uint32_t SM_MISC = SM_ZT + 64 * ZP * 4;    // ln params of both sequences, barriers
 constexpr uint32_t SM_TOTAL = SM_MISC + 2048;
 
@@ -87,10 +89,13 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  // token-thread roles for the LayerNorm phase (threads 0..63): sequence ts, token index tt (0-15 K side, 16-31 Q side)
-  const int ts = tid >> 5, tt = tid & 31;
+  // LayerNorm-phase roles (all 128 threads): token row = tid >> 1 (sequence ts, token tt: 0-15 K side, 16-31 Q side),
+  // column half ch = tid & 1; the two threads of a row are adjacent lanes and exchange partial sums by shuffle.  Each
+  // warp is uniformly K side or Q side: warp 0 = seq0 K, 1 = seq0 Q, 2 = seq1 K, 3 = seq1 Q.
+  const int trow_id = tid >> 1, ch = tid & 1;
+  const int ts = trow_id >> 5, tt = trow_id & 31;
   const int bh_tok = 2 * blockIdx.x + ts;
-  const bool tok_valid = tid < 64 && bh_tok < p.BH;
+  const bool tok_valid = bh_tok < p.BH;
 
   auto issue_loads = [&](int it, int slot) {  // K_it, V_it (if it < NC) and Q_{it-1} (if it > 0) of both sequences
     uint32_t bytes = 0;
@@ -151,7 +156,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t tok = sbase + SM_TOK + slot * 8192;
     const uint32_t vt = sbase + SM_V + slot * 4096;
     float eta_i = 0.f;
-    if (has_k && tok_valid && tt < 16) eta_i = __bfloat162float(p.last_eta[((size_t)bh_tok * NC + it) * CS + tt]);
+    if (has_k && tok_valid && tt < 16) eta_i = __bfloat162float(p.last_eta[((size_t)bh_tok * NC + it) * CS + tt]);  // both threads of the row
 
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
     if (tid == 0 && it < NC) issue_loads(it + 1, slot ^ 1);
@@ -177,77 +182,74 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        zt[(s_row * 32 + i) * ZP + fo] = __uint_as_float(vk[i]) + b1r;
-        zt[(s_row * 32 + 16 + i) * ZP + fo] = __uint_as_float(vq[i]) + b1r;
+        zt[zidx(s_row * 32 + i, fo)] = __uint_as_float(vk[i]) + b1r;
+        zt[zidx(s_row * 32 + 16 + i, fo)] = __uint_as_float(vq[i]) + b1r;
       }
     }
     tc_fence_before();
     __syncthreads();
 
-    // ---- EW-B: LayerNorm per token row (threads 0..63)
+    // ---- EW-B: LayerNorm per token row: 2 threads per row (32 columns each), all 4 warps
     if (tok_valid && ((tt < 16) ? has_k : has_q)) {
-      float z[64];
-      const float* zr = zt + (ts * 32 + tt) * ZP;
-      float mu = 0.f;
+      float z[32];
+      float* zr = zt + (ts * 32 + tt) * ZP + ch * 33;
+      float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-      for (int f = 0; f < 64; ++f) { z[f] = zr[f]; mu += z[f]; }
-      mu *= (1.f / 64.f);
-      float var = 0.f;
-#pragma unroll
-      for (int f = 0; f < 64; ++f) { z[f] -= mu; var = fmaf(z[f], z[f], var); }
-      const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-8f);
-      const float* gw = lnw + ts * 64;
-      const float* gb = lnb + ts * 64;
+      for (int f = 0; f < 32; ++f) { z[f] = zr[f]; a1 += z[f]; a2 = fmaf(z[f], z[f], a2); }
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+      const float mu = a1 * (1.f / 64.f);
+      const float rstd = rsqrtf(fmaxf(a2 * (1.f / 64.f) - mu * mu, 0.f) + 1e-8f);
+      const float* gw = lnw + ts * 64 + 32 * ch;
+      const float* gb = lnb + ts * 64 + 32 * ch;
       if (tt < 16) {
         const int r = 16 * ts + tt;  // row of K in the token tile and of V in the V tile
+        float g[32];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t kk[4], vv[4];
-          ld_shared_v4(tok + sw128_off(r, c), kk[0], kk[1], kk[2], kk[3]);
-          ld_shared_v4(vt + sw128_off(r, c), vv[0], vv[1], vv[2], vv[3]);
+          ld_shared_v4(tok + sw128_off(r, 4 * ch + c), kk[0], kk[1], kk[2], kk[3]);
+          ld_shared_v4(vt + sw128_off(r, 4 * ch + c), vv[0], vv[1], vv[2], vv[3]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int f = 8 * c + 2 * e;
-            const float x0 = z[f] * rstd, x1 = z[f + 1] * rstd;
-            const float g0 = (fmaf(gw[f], x0, gb[f]) - (bf16_lo(vv[e]) - bf16_lo(kk[e]))) * gw[f];
-            const float g1 = (fmaf(gw[f + 1], x1, gb[f + 1]) - (bf16_hi(vv[e]) - bf16_hi(kk[e]))) * gw[f + 1];
-            s1 += g0 + g1;
-            s2 = fmaf(g0, x0, fmaf(g1, x1, s2));
-            z[f] = x0; z[f + 1] = x1;
-            // stash gxh in the transpose row (it is re-read below); avoids a second smem pass over K/V
-            const_cast<float*>(zr)[f] = g0;
-            const_cast<float*>(zr)[f + 1] = g1;
+            z[f] = (z[f] - mu) * rstd; z[f + 1] = (z[f + 1] - mu) * rstd;
+            g[f] = (fmaf(gw[f], z[f], gb[f]) - (bf16_lo(vv[e]) - bf16_lo(kk[e]))) * gw[f];
+            g[f + 1] = (fmaf(gw[f + 1], z[f + 1], gb[f + 1]) - (bf16_hi(vv[e]) - bf16_hi(kk[e]))) * gw[f + 1];
+            s1 += g[f] + g[f + 1];
+            s2 = fmaf(g[f], z[f], fmaf(g[f + 1], z[f + 1], s2));
           }
         }
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
         const float sc = -eta_i * rstd * (1.f / 64.f);
-        float* zw = const_cast<float*>(zr);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int f = 8 * c + 2 * e;
-            const float d0 = (fmaf(64.f, zw[f], -s1) - z[f] * s2) * sc;
-            const float d1 = (fmaf(64.f, zw[f + 1], -s1) - z[f + 1] * s2) * sc;
-            zw[f] = d0; zw[f + 1] = d1;   // fp32 G = -eta * gradZ1 for the b1 column sums
+            const float d0 = (fmaf(64.f, g[f], -s1) - z[f] * s2) * sc;
+            const float d1 = (fmaf(64.f, g[f + 1], -s1) - z[f + 1] * s2) * sc;
+            zr[f] = d0; zr[f + 1] = d1;   // fp32 G = -eta * gradZ1 for the b1 column sums
             o[e] = pack_bf16(d0, d1);
           }
-          st_shared_v4(sbase + SM_GT + ts * 4096 + sw128_off(r, c), o[0], o[1], o[2], o[3]);
+          st_shared_v4(sbase + SM_GT + ts * 4096 + sw128_off(r, 4 * ch + c), o[0], o[1], o[2], o[3]);
         }
       } else {
         const int tq = tt - 16;
         const int r = 32 + 16 * ts + tq;  // row of Q_{it-1} in the token tile
-        __nv_bfloat16* og = p.Out + (((size_t)bh_tok * NC + (it - 1)) * CS + tq) * F;
+        __nv_bfloat16* og = p.Out + (((size_t)bh_tok * NC + (it - 1)) * CS + tq) * F + 32 * ch;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t qq[4], o[4];
-          ld_shared_v4(tok + sw128_off(r, c), qq[0], qq[1], qq[2], qq[3]);
+          ld_shared_v4(tok + sw128_off(r, 4 * ch + c), qq[0], qq[1], qq[2], qq[3]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int f = 8 * c + 2 * e;
-            o[e] = pack_bf16(bf16_lo(qq[e]) + fmaf(gw[f], z[f] * rstd, gb[f]),
-                             bf16_hi(qq[e]) + fmaf(gw[f + 1], z[f + 1] * rstd, gb[f + 1]));
+            o[e] = pack_bf16(bf16_lo(qq[e]) + fmaf(gw[f], (z[f] - mu) * rstd, gb[f]),
+                             bf16_hi(qq[e]) + fmaf(gw[f + 1], (z[f + 1] - mu) * rstd, gb[f + 1]));
           }
           *reinterpret_cast<uint4*>(og + 8 * c) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -270,7 +272,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     {
       float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc += zt[(s_row * 32 + i) * ZP + fo];
+      for (int i = 0; i < 16; ++i) acc += zt[zidx(s_row * 32 + i, fo)];
       b1r += acc;
     }
     mbar_wait(mma_bar, mma_phase);

@@ -210,37 +210,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1;
     mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1;
     mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
-    mbar_wait(bar_qd, ph_qd); ph_qd ^= 1;
-    mbar_wait(bar_xb, ph_xb); ph_xb ^= 1;
     __syncthreads();  // b2t / etas visible
       TICK(0);
 
-    // ===== apply the Q-side contribution of step t to the carried gradient (outer products of the factor tiles written
-    //       by ttt_mlp_bwd_q_kernel):  dW2 += Xbar2^T dZbar2 ;  dW1^T += dZbar1^T Q
-    if (tid == 0) {
-      tc_fence_after();
-      mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sA, sbase + SM_TT0, true, 64, true);
-      mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TQ, true, 64, true);
-      tc_commit(mma_bar);
-    }
-    MMA_WAIT();
-
     if (has_k) {
-      // ===== A0 [H]: bf16 copies of the carried gradient accumulators: CW1 -> sA, CW2 -> sB
-      {
-        float v[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
-          tc_wait_ld();
-          st_row32(sbase + sA, j, 4 * c, v);
-          tmem_ld32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
-          tc_wait_ld();
-          st_row32(sbase + sB, j, 4 * c, v);
-        }
-      }
-      PHASE_SYNC();
-      TICK(1);
       // ===== A1 MMA: R1 = W1 . K^T -> (S0,S1)
       if (tid == 0) {
         tc_fence_after();
@@ -271,6 +244,33 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       PHASE_SYNC();
       TICK(3);
+      mbar_wait(bar_qd, ph_qd); ph_qd ^= 1;
+      mbar_wait(bar_xb, ph_xb); ph_xb ^= 1;
+      // ===== apply the Q-side contribution of step t to the carried gradient (outer products of the factor tiles written
+      //       by ttt_mlp_bwd_q_kernel):  dW2 += Xbar2^T dZbar2 ;  dW1^T += dZbar1^T Q
+      if (tid == 0) {
+        tc_fence_after();
+        mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sA, sbase + SM_TT0, true, 64, true);
+        mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TQ, true, 64, true);
+        tc_commit(mma_bar);
+      }
+      MMA_WAIT();
+
+      // ===== A0 [H]: bf16 copies of the carried gradient accumulators: CW1 -> sA, CW2 -> sB
+      {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+          st_row32(sbase + sA, j, 4 * c, v);
+          tmem_ld32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
+          tc_wait_ld();
+          st_row32(sbase + sB, j, 4 * c, v);
+        }
+      }
+      PHASE_SYNC();
+      TICK(1);
       // ===== A3 MMA: R2: Z2 = X2 . W2 -> S2 ; B5: acc5 = X2 . CW2 -> S3
       if (tid == 0) {
         tc_fence_after();
@@ -664,8 +664,10 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   TB_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   Side& sd = sides[dev & 63];
   if (!sd.sT) {
-    TB_TRY(cudaStreamCreateWithFlags(&sd.sT, cudaStreamNonBlocking), "side stream");
-    TB_TRY(cudaStreamCreateWithFlags(&sd.sQ, cudaStreamNonBlocking), "side stream");
+    int prio_lo = 0, prio_hi = 0;  // recompute work must never delay the CTAs of the sequential kernel: lowest priority
+    TB_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), "priority range");
+    TB_TRY(cudaStreamCreateWithPriority(&sd.sT, cudaStreamNonBlocking, prio_lo), "side stream");
+    TB_TRY(cudaStreamCreateWithPriority(&sd.sQ, cudaStreamNonBlocking, prio_lo), "side stream");
     TB_TRY(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming), "event");
     for (int i = 0; i < kRing; ++i) {
       TB_TRY(cudaEventCreateWithFlags(&sd.evT[i], cudaEventDisableTiming), "event");
