@@ -69,14 +69,17 @@ for rep in range(2):
     out.backward(bf(d['dOut']))
     torch.cuda.synchronize()
     t = buf.cpu().tolist()
-    bn = ['top','apply+A0 cw','A1 mma','A2 gelu3','A3 mma','A4 tok','A56 mma','A56 ew','A7 mma','A8 tok','A9 mma','A10 ew','A11 mma','A12 tok']
+    bn = ['top','apply+A0 cw','A1 mma','A2 gelu3','A3 mma','A4 tok','A56 mma','A56 ew','A7 mma','A8 tok','A9 mma','A10 ew','A11 mma','A12 tok','PROLOGUE(total)','looptail','EPILOGUE(total)']
     if rep == 1:
         for ob in (0,1):
             tot = sum(t[ob*64:ob*64+14])
-            print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn)}, flush=True)
+            print('   prologue cycles', t[ob*64+14], 'epilogue cycles', t[ob*64+16], flush=True)
+            print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn[:14])}, flush=True)
     buf.zero_()
 """ % (ROOT, ROOT, ROOT),
     "timeline": """
+import os
+if os.environ.get('TTT_TIMELINE_DBG'): os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
 import torch, sys, json
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
@@ -105,7 +108,7 @@ for ev in evs[:70]:
     nm = 'FWD ' if 'fwd_kernelILb0' in ev.name else ('TRAJ' if 'fwd_kernelILb1' in ev.name else ('Q   ' if 'bwd_q' in ev.name else 'K   '))
     print(nm, 'start %%8.1f us  dur %%7.1f us' %% ((ev.time_range.start - t0), ev.time_range.end - ev.time_range.start), flush=True)
 print('total span us', evs[-1].time_range.end - t0)
-""" % (ROOT, ROOT),
+""" % (ROOT, ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

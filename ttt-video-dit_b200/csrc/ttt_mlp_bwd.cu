@@ -73,6 +73,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int half = warp >> 2;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   const int j = tid;
+  TICK_DECL(22, 224)
 
   float* lnw = reinterpret_cast<float*>(smem + SM_MISC);  // [64]
   float* lnb = lnw + 64;
@@ -126,12 +127,21 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t v[32];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
+      if (p.first) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = p.first ? 0u : __float_as_uint(p.dW1s[((size_t)bh * HID + j) * F + 32 * c + i]);
-      tmem_st32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, v);
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+        tmem_st32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, v);
+        tmem_st32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, v);
+      } else {
+        const uint4* s1 = reinterpret_cast<const uint4*>(p.dW1s + ((size_t)bh * HID + j) * F + 32 * c);
+        const uint4* s2 = reinterpret_cast<const uint4*>(p.dW2s + ((size_t)bh * HID + j) * F + 32 * c);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = p.first ? 0u : __float_as_uint(p.dW2s[((size_t)bh * HID + j) * F + 32 * c + i]);
-      tmem_st32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, v);
+        for (int i = 0; i < 8; ++i) { const uint4 q = s1[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+        tmem_st32(tmem + lane_addr + TM_DW1 + 64 * half + 32 * c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const uint4 q = s2[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+        tmem_st32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, v);
+      }
     }
     tc_wait_st();
   }
@@ -173,7 +183,6 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
 
-  TICK_DECL(22, 224)
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
   float nb1 = p.b1img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * HID + j], nb2 = 0.f;
@@ -184,6 +193,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     nq2 = p.qb2[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * F + tid];
     if (p.t_hi < p.NC) neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)p.t_hi * CS + tid];
   }
+  TICK(14);  // prologue
   for (int t = p.t_hi; t >= p.t_lo; --t) {
     const bool has_k = true;
     const size_t slot = (size_t)(t - p.t0);
@@ -568,7 +578,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   }
 
-  TICK_DUMP(22, p.dbg);
+  TICK(15);  // (loop tail)
   // ---- epilogue: carried gradient -> scratch (or final outputs), LN parameter gradients
   tc_fence_after();
   {
@@ -582,14 +592,15 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; ++i) p.dW1[((size_t)bh * F + 32 * c + i) * HID + j] = v[i];  // [f][j] layout
       } else {
+        float4* d1 = reinterpret_cast<float4*>(p.dW1s + ((size_t)bh * HID + j) * F + 32 * c);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) p.dW1s[((size_t)bh * HID + j) * F + 32 * c + i] = v[i];
+        for (int i = 0; i < 8; ++i) d1[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
       tmem_ld32(tmem + lane_addr + TM_DW2 + 64 * half + 32 * c, reinterpret_cast<uint32_t*>(v));
       tc_wait_ld();
-      float* dst = (fin ? p.dW2 : p.dW2s) + ((size_t)bh * HID + j) * F + 32 * c;
+      float4* dst = reinterpret_cast<float4*>((fin ? p.dW2 : p.dW2s) + ((size_t)bh * HID + j) * F + 32 * c);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dst[i] = v[i];
+      for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
     (fin ? p.db1 : p.db1s)[(size_t)bh * HID + j] = db1r;
     if (tid < 64) (fin ? p.db2 : p.db2s)[(size_t)bh * 64 + tid] = db2c[tid];
@@ -598,6 +609,8 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       atomicAdd(&p.dlnb[(size_t)bh * 64 + tid], dbet[tid]);
     }
   }
+  TICK(16);  // epilogue stores
+  TICK_DUMP(22, p.dbg);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
