@@ -258,6 +258,13 @@ def main():
     flop_per_step = B * H * NC * U_FLOP * (FWD_U + (BWD_U if mode == "fwdbwd" else 0))
     burst, sustained, src = peaks()
     achieved = flop_per_step / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
+        tj = json.load(open(tpath)).get(mode)
+        if tj:
+            per_launch_units = B * H * (NC if mode == "fwd" else min(G, NC))
+            traffic = {"bytes_per_launch": tj["bytes_per_head_minibatch"] * per_launch_units, "kernel": tj["kernel"], "source": tj["source"]}
     line = {
         "metric": f"video-tokens/sec TTT-MLP layer-direction ({'fwd+bwd' if mode == 'fwdbwd' else 'fwd'})",
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -271,8 +278,9 @@ def main():
         "gpu_launches": n_launch,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                     "traffic": None, "peak_source": src + ", burst figure (op timed alone)",
-                     "kernel_ms": kernel_ms, "algorithmic_flop_per_step": flop_per_step},
+                     "traffic": traffic, "peak_source": src + ", burst figure (op timed alone)",
+                     "kernel_ms": kernel_ms, "algorithmic_flop_per_step": flop_per_step,
+                     "scope": "whole step (all our kernels of the op: 7U fwd + 15U bwd per head per mini-batch; recompute not counted)"},
     }
     if not args.no_cpu_baseline:
         v, dt, sample = cpu_eager_tokens_per_s(H, mode, sample_nc=3, reps=1)
