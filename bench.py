@@ -149,7 +149,6 @@ def main():
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    from oracle import ttt_oracle as O  # only for synthetic input generation + the cpu_baseline leg
     from ttt_video_dit_b200 import mlp_tk
 
     have_bwd = mlp_tk.HAVE_BACKWARD
