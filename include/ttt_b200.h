@@ -65,6 +65,20 @@ int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, cons
                             float* W1_ckpt, float* b1_ckpt, float* W1_last, float* b1_last, void* Out,
                             int B, int H, int NC, int checkpoint_group_size, void* stream);
 
+/* TTT-Linear backward scan.  Replaces the Triton launch in ttt/models/ssm/linear_triton.py:203-246 (kernel
+ * ttt/models/ssm/kernels/linear_backward.py:207-520) and its eight per-group spill buffers (linear_triton.py:168-182).
+ * W1_ckpt/b1_ckpt are the checkpoints the forward wrote ([B,H,K,64,64] / [B,H,K,64], K = ceil(NC/group)).  Outputs:
+ * d_ln_weight/d_ln_bias f32 [B,H,64] per-batch partials (overwritten; the reference sums them over B after the kernel,
+ * linear_triton.py:251-252), dW1 f32 [B,H,64,64], db1 f32 [B,H,64] (w.r.t. the initial state), d_last_eta f32
+ * [B,H,NC,16] (gradient of the last eta row, the only row the scan reads), dXQ/dXK/dXV bf16 [B,H,NC,16,64].
+ * workspace: ttt_b200_linear_backward_workspace_bytes(B,H,NC,group) bytes of device memory (state trajectory images). */
+size_t ttt_b200_linear_backward_workspace_bytes(int B, int H, int NC, int checkpoint_group_size);
+int ttt_b200_linear_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta,
+                             const float* ln_weight, const float* ln_bias, const float* W1_ckpt, const float* b1_ckpt,
+                             const void* dOut, float* d_ln_weight, float* d_ln_bias, float* dW1, float* db1,
+                             float* d_last_eta, void* dXQ, void* dXK, void* dXV, void* workspace,
+                             size_t workspace_bytes, int B, int H, int NC, int checkpoint_group_size, void* stream);
+
 /* Non-causal self-attention forward over one segment, head_dim 64.  Replaces F.scaled_dot_product_attention(q, k, v,
  * attn_mask=None, dropout_p=0, is_causal=False) at ttt/models/cogvideo/dit.py:196-198.  q/k/v/out: bf16 [B, T, H, 64]
  * contiguous = the "b t (h d)" output of the q/k/v Linears, so the reference's rearranges around SDPA disappear.

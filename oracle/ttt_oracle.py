@@ -319,6 +319,76 @@ def ttt_linear_primal_forward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1):
     return out, (W1, b1)
 
 
+def ttt_linear_step_backward(XQ, XK, XV, W1, b1, W1n, b1n, last_eta, ln_w, ln_b, dW1n, db1n, dO):
+    """Closed-form backward of one primal TTT-Linear step (the algebra of kernels/linear_backward.py:73-197; the MLP
+    step above with the second layer dropped).  W1/b1 = state before the step, W1n/b1n = after; dW1n/db1n = gradient
+    w.r.t. the state after the step.  Returns (dln_w, dln_b, dW1, db1, dXQ, dXV, dXK, dlast_eta[B,H,CS,1])."""
+    H, Fd = XQ.shape[1], XQ.shape[-1]
+    g = ln_w.reshape(H, 1, Fd); bt = ln_b.reshape(H, 1, Fd)
+    eta = last_eta
+    # recompute the forward intermediates
+    Z1 = XK @ W1 + b1
+    mu = Z1.mean(-1, keepdim=True); std_f = torch.sqrt(Z1.var(-1, keepdim=True, unbiased=False) + LN_EPS)
+    xhat_f = (Z1 - mu) / std_f
+    go = g * xhat_f + bt - (XV - XK)
+    gxh = go * g
+    gZ1 = (1.0 / Fd) * (Fd * gxh - gxh.sum(-1, keepdim=True) - xhat_f * (gxh * xhat_f).sum(-1, keepdim=True)) / std_f
+    Z1b = XQ @ W1n + b1n
+    mu_o = Z1b.mean(-1, keepdim=True); std_o = torch.sqrt(Z1b.var(-1, keepdim=True, unbiased=False) + LN_EPS)
+    xhat_o = (Z1b - mu_o) / std_o
+    # output LayerNorm + Q side
+    dbeta_o = dO.sum(-2, keepdim=True).sum(0)
+    dgamma_o = (dO * xhat_o).sum(-2, keepdim=True).sum(0)
+    dxh = dO * g
+    dZ1b = (1.0 / Fd) * (Fd * dxh - dxh.sum(-1, keepdim=True) - xhat_o * (dxh * xhat_o).sum(-1, keepdim=True)) / std_o
+    db1n = db1n + dZ1b.sum(-2, keepdim=True)
+    dW1n = dW1n + XQ.transpose(-2, -1) @ dZ1b
+    dXQ = dO + dZ1b @ W1n.transpose(-2, -1)
+    # update rule  W1n = W1 - (eta XK)^T gZ1,  b1n = b1 - sum(eta gZ1)
+    dgZ1 = -(eta * XK) @ dW1n - eta * db1n
+    T1 = gZ1 @ dW1n.transpose(-2, -1)
+    dXK_u = -T1 * eta
+    deta = -(T1 * XK).sum(-1, keepdim=True) - (db1n * gZ1).sum(-1, keepdim=True)
+    # backward through gZ1 = ln_fused_l2_bwd(Z1, XV - XK)
+    dgxh = (1.0 / std_f) * (dgZ1 + (-1.0 / Fd) * (dgZ1.sum(-1, keepdim=True) + xhat_f * (dgZ1 * xhat_f).sum(-1, keepdim=True)))
+    dy = g * dgxh
+    dgamma_f = (go * dgxh + dy * xhat_f).sum(-2, keepdim=True).sum(0)
+    dbeta_f = dy.sum(-2, keepdim=True).sum(0)
+    dxh_f = dy * g + (-1.0 / (Fd * std_f)) * (gxh * (dgZ1 * xhat_f).sum(-1, keepdim=True)
+                                             + dgZ1 * (gxh * xhat_f).sum(-1, keepdim=True))
+    dstd = (-dxh_f * xhat_f - dgZ1 * gZ1) / std_f
+    dZ1 = dxh_f / std_f + (1.0 / Fd) * (dstd.sum(-1, keepdim=True) * xhat_f - dxh_f.sum(-1, keepdim=True) / std_f)
+    dtarget = -dy
+    dXK = -dtarget + dXK_u + dZ1 @ W1.transpose(-2, -1)
+    dXV = dtarget
+    dW1 = dW1n + XK.transpose(-2, -1) @ dZ1
+    db1 = db1n + dZ1.sum(-2, keepdim=True)
+    return ((dgamma_o + dgamma_f).reshape(H, Fd), (dbeta_o + dbeta_f).reshape(H, Fd), dW1, db1, dXQ, dXV, dXK, deta)
+
+
+def ttt_linear_primal_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, dOut):
+    """Whole-sequence analytic backward of TTT-Linear (keeps every state; small cases only).  last_eta [B,H,NC,CS,1]."""
+    B, H, NC, CS, Fd = XQ.shape
+    g = ln_w.reshape(H, 1, Fd); bt = ln_b.reshape(H, 1, Fd)
+    states = [(W1, b1)]
+    for n in range(NC):
+        W, b = states[-1]
+        k, v, e = XK[:, :, n], XV[:, :, n], last_eta[:, :, n]
+        gZ1 = ln_fused_l2_bwd(k @ W + b, v - k, g, bt)
+        states.append((W - (e * k).transpose(-1, -2) @ gZ1, b - (e * gZ1).sum(-2, keepdim=True)))
+    dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1)
+    dXQ = torch.empty_like(XQ); dXK = torch.empty_like(XK); dXV = torch.empty_like(XV)
+    deta = torch.empty_like(last_eta)
+    dlw = torch.zeros(H, Fd, dtype=XQ.dtype); dlb = torch.zeros(H, Fd, dtype=XQ.dtype)
+    for n in reversed(range(NC)):
+        r = ttt_linear_step_backward(XQ[:, :, n], XK[:, :, n], XV[:, :, n], *states[n], *states[n + 1], last_eta[:, :, n],
+                                     ln_w, ln_b, dW1, db1, dOut[:, :, n])
+        dlw += r[0]; dlb += r[1]
+        dW1, db1 = r[2], r[3]
+        dXQ[:, :, n], dXV[:, :, n], dXK[:, :, n], deta[:, :, n] = r[4:8]
+    return dict(dln_w=dlw, dln_b=dlb, dW1=dW1, db1=db1, dXQ=dXQ, dXV=dXV, dXK=dXK, dlast_eta=deta)
+
+
 # --------------------------------------------------------------------------------------
 # Autograd-of-eager gradient oracle (what TkMLP.backward / TritonLinear.backward must match)
 # --------------------------------------------------------------------------------------

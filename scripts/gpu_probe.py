@@ -48,9 +48,9 @@ import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import _lib, mlp_tk
-buf = torch.zeros(128, dtype=torch.int32, device='cuda')
+buf = torch.zeros(4096, dtype=torch.int32, device='cuda')
 print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
-B,H,NC,G = 1,48,64,16
+B,H,NC,G = 1,48,int(os.environ.get('TTT_TIMING_NC','64')),16
 d = O.make_inputs(B,H,NC,seed=1)
 bf = lambda t: t.to(torch.bfloat16).cuda()
 prm = [d[k].cuda().requires_grad_(True) for k in ('ln_w','ln_b','W1','b1','W2','b2')]
@@ -75,6 +75,15 @@ for rep in range(2):
             tot = sum(t[ob*64:ob*64+14])
             print('   prologue cycles', t[ob*64+14], 'epilogue cycles', t[ob*64+16], flush=True)
             print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn[:14])}, flush=True)
+        print('per-block K-kernel cycles (sorted):', sorted(t[128:128+48]), flush=True)
+        print('smid of block b:', t[192:192+48], flush=True)
+        ngr = (NC + G - 1) // G
+        base = None
+        for gi in range(min(ngr, 27) - 1, -1, -1):
+            st = [x & 0xffffffff for x in t[512+gi*128:512+gi*128+48]]; en = [x & 0xffffffff for x in t[512+gi*128+64:512+gi*128+64+48]]
+            if base is None: base = min(st)
+            ss = sorted((x-base)/1e3 for x in st); ee = sorted((x-base)/1e3 for x in en)
+            print('group %%2d: first start %%8.1f last start %%8.1f | first end %%8.1f last end %%8.1f  (us)' %% (gi, ss[0], ss[-1], ee[0], ee[-1]), flush=True)
     buf.zero_()
 """ % (ROOT, ROOT, ROOT),
     "timeline": """
@@ -109,6 +118,33 @@ for ev in evs[:70]:
     print(nm, 'start %%8.1f us  dur %%7.1f us' %% ((ev.time_range.start - t0), ev.time_range.end - ev.time_range.start), flush=True)
 print('total span us', evs[-1].time_range.end - t0)
 """ % (ROOT, ROOT, ROOT),
+    "lin_bwd": """
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+import test_gpu_linear_backward as T
+for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,2,3,2),(2,2,7,3),(1,3,20,16),(1,2,300,16)]:
+    d = O.make_inputs(B,H,NC,CS=16,seed=70+NC,base_lr=1.0,linear=True)
+    try:
+        print((B,H,NC,G), {k: float('%%.2e' %% v) for k,v in T.errors(d,G).items()}, flush=True)
+    except Exception as ex:
+        print((B,H,NC,G), 'EXC', repr(ex)[:300], flush=True); break
+import time
+B,H,NC,G = 1,48,1128,16
+d = O.make_inputs(B,H,NC,CS=16,seed=1,base_lr=1.0,linear=True)
+dev='cuda'; bf = lambda t: t.to(torch.bfloat16).to(dev)
+prm = [d[k].to(dev).requires_grad_(True) for k in ('ln_w','ln_b','W1','b1')]
+q,v,k,e = [bf(d[n]).requires_grad_(True) for n in ('XQ','XV','XK','eta')]
+go = bf(d['dOut'])
+from ttt_video_dit_b200 import linear_triton
+for rep in range(3):
+    torch.cuda.synchronize(); t0=time.time()
+    out = linear_triton.TritonLinear.apply(*prm, q, v, k, e, G)
+    torch.cuda.synchronize(); t1=time.time()
+    out.backward(go)
+    torch.cuda.synchronize(); t2=time.time()
+    print('linear NC=1128 B=1: fwd %%.3f ms  bwd %%.3f ms' %% ((t1-t0)*1e3, (t2-t1)*1e3), flush=True)
+""" % (ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

@@ -16,6 +16,9 @@ _SIGS = {
     "ttt_b200_mlp_backward_workspace_bytes": ([_i, _i, _i], ctypes.c_size_t),
     "ttt_b200_mlp_backward": ([_vp] * 4 + [_fp] * 2 + [_fp] * 4 + [_vp] + [_fp] * 6 + [_vp] * 4 + [_vp, ctypes.c_size_t] + [_i] * 4 + [_vp], ctypes.c_int),
     "ttt_b200_linear_forward": ([_vp] * 4 + [_fp] * 2 + [_fp] * 2 + [_fp] * 4 + [_vp] + [_i] * 4 + [_vp], ctypes.c_int),
+    "ttt_b200_linear_backward_workspace_bytes": ([_i] * 4, ctypes.c_size_t),
+    "ttt_b200_linear_backward": ([_vp] * 4 + [_fp] * 4 + [_vp] + [_fp] * 5 + [_vp] * 4 + [ctypes.c_size_t] + [_i] * 4 + [_vp],
+                                 ctypes.c_int),
     "ttt_b200_attention_forward": ([_vp] * 4 + [_i] * 3 + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_gate_forward": ([_vp, _vp, _fp, _fp, _vp, _vp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_gate_backward": ([_vp, _vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 6 + [_vp], ctypes.c_int),

@@ -112,6 +112,30 @@ int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, cons
                   "ttt_b200_linear_forward");
 }
 
+size_t ttt_b200_linear_backward_workspace_bytes(int B, int H, int NC, int G) {
+  if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) return 0;
+  return tb::linear_backward_workspace_bytes(B, H, NC, G > NC ? NC : G);
+}
+
+int ttt_b200_linear_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_weight,
+                             const float* ln_bias, const float* W1_ckpt, const float* b1_ckpt, const void* dOut,
+                             float* d_ln_weight, float* d_ln_bias, float* dW1, float* db1, float* d_last_eta, void* dXQ,
+                             void* dXK, void* dXV, void* workspace, size_t workspace_bytes, int B, int H, int NC,
+                             int checkpoint_group_size, void* stream) {
+  if (!XQ || !XK || !XV || !last_eta || !ln_weight || !ln_bias || !W1_ckpt || !b1_ckpt || !dOut || !d_ln_weight ||
+      !d_ln_bias || !dW1 || !db1 || !d_last_eta || !dXQ || !dXK || !dXV || !workspace)
+    return fail(-1, "ttt_b200_linear_backward: null pointer argument");
+  if (B <= 0 || H <= 0 || NC <= 0 || checkpoint_group_size <= 0)
+    return fail(-2, "ttt_b200_linear_backward: B, H, NC and checkpoint_group_size must be positive");
+  if (workspace_bytes < ttt_b200_linear_backward_workspace_bytes(B, H, NC, checkpoint_group_size))
+    return fail(-4, "ttt_b200_linear_backward: workspace too small (see ttt_b200_linear_backward_workspace_bytes)");
+  if (int rc = bind_device(XQ)) return rc;
+  return cuda_ret(tb::launch_linear_backward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, dOut,
+                                             d_ln_weight, d_ln_bias, dW1, db1, d_last_eta, dXQ, dXK, dXV, workspace,
+                                             workspace_bytes, B, H, NC, checkpoint_group_size, (cudaStream_t)stream),
+                  "ttt_b200_linear_backward");
+}
+
 int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void* out, int B, int T, int H, float scale,
                                void* stream) {
   if (!q || !k || !v || !out) return fail(-1, "ttt_b200_attention_forward: null pointer argument");

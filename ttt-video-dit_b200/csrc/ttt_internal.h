@@ -61,6 +61,16 @@ cudaError_t launch_linear_forward(const void* XQ, const void* XK, const void* XV
                                   const float* ln_b, const float* W1, const float* b1, float* W1c, float* b1c,
                                   float* W1o, float* b1o, void* Out, int B, int H, int NC, int ckpt_group,
                                   cudaStream_t stream);
+cudaError_t launch_linear_trajectory(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                     const float* ln_b, const float* W1s, const float* b1s, long long w_stride,
+                                     long long b_stride, uint8_t* img, float* b1img, int img_slots, int B, int H, int NC,
+                                     int t0, int nsteps, cudaStream_t stream);
+size_t linear_backward_workspace_bytes(int B, int H, int NC, int G);
+cudaError_t launch_linear_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                   const float* ln_b, const float* W1c, const float* b1c, const void* dOut, float* dlnw,
+                                   float* dlnb, float* dW1, float* db1, float* dEta, void* dXQ, void* dXK, void* dXV,
+                                   void* workspace, size_t workspace_bytes, int B, int H, int NC, int G,
+                                   cudaStream_t stream);
 }  // namespace tb
 
 namespace tb {

@@ -44,15 +44,23 @@ struct LinParams {
   float *W1o, *b1o;               // final state (may be null)
   __nv_bfloat16* Out;             // [B,H,NC,16,64]
   int BH, H, NC, ckpt_group, K;
+  // trajectory mode (backward recompute, ttt_linear_bwd.cu): run steps t0 .. t0+nsteps-1 (K side only) from the state
+  // at W1 + bh*w_stride (b1 + bh*b_stride) and save the bf16 operand image of the state BEFORE step t0+i in slot i and
+  // the state after the last step in slot nsteps: img [pairs][img_slots] x 16 KB, b1img [pairs][img_slots][128] fp32
+  long long w_stride, b_stride;
+  int t0, nsteps, img_slots;
+  uint8_t* img;
+  float* b1img;
 };
 
+template <bool kTraj>
 __global__ void __launch_bounds__(NT, 1)
 ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const LinParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int NC = p.NC;
+  const int NC = kTraj ? p.nsteps : p.NC;  // steps this launch runs (trajectory mode: a window of the sequence)
   const int s_row = tid >> 6;            // which of the two stacked sequences this W1^T row belongs to
   const int fo = tid & 63;               // output feature of this row
   const int bh_row = 2 * blockIdx.x + s_row;
@@ -102,26 +110,26 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       if (2 * (int)blockIdx.x + s >= p.BH) continue;
       if (it < NC) bytes += 4096;
-      if (it > 0) bytes += 2048;
+      if (!kTraj && it > 0) bytes += 2048;
     }
     mbar_expect_tx(&tma_bar[slot], bytes);
     for (int s = 0; s < 2; ++s) {
       const int bh = 2 * blockIdx.x + s;
       if (bh >= p.BH) continue;
-      const int row0 = (bh * NC) * CS;
+      const int row0 = (bh * p.NC + (kTraj ? p.t0 : 0)) * CS;
       if (it < NC) {
         tma_load_2d(smem + SM_TOK + slot * 8192 + s * 2048, &tmK, 0, row0 + it * CS, &tma_bar[slot]);
         tma_load_2d(smem + SM_V + slot * 4096 + s * 2048, &tmV, 0, row0 + it * CS, &tma_bar[slot]);
       }
-      if (it > 0) tma_load_2d(smem + SM_TOK + slot * 8192 + 4096 + s * 2048, &tmQ, 0, row0 + (it - 1) * CS, &tma_bar[slot]);
+      if (!kTraj && it > 0) tma_load_2d(smem + SM_TOK + slot * 8192 + 4096 + s * 2048, &tmQ, 0, row0 + (it - 1) * CS, &tma_bar[slot]);
     }
   };
   if (tid == 0) issue_loads(0, 0);
 
   // ---- initial state -> TMEM accumulator + bf16 operand copy (+ checkpoint 0)
-  float b1r = row_valid ? p.b1[(size_t)bh_row * F + fo] : 0.f;
+  float b1r = row_valid ? p.b1[(size_t)bh_row * p.b_stride + fo] : 0.f;
   {
-    const float* W1g = p.W1 + (size_t)(row_valid ? bh_row : 0) * F * F;
+    const float* W1g = p.W1 + (size_t)(row_valid ? bh_row : 0) * p.w_stride;
     uint32_t v[32];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -152,11 +160,20 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   for (int it = 0; it <= NC; ++it) {
     const int slot = it & 1;
-    const bool has_k = it < NC, has_q = it > 0;
+    const bool has_k = it < NC, has_q = !kTraj && it > 0;
     const uint32_t tok = sbase + SM_TOK + slot * 8192;
     const uint32_t vt = sbase + SM_V + slot * 4096;
     float eta_i = 0.f;
-    if (has_k && tok_valid && tt < 16) eta_i = __bfloat162float(p.last_eta[((size_t)bh_tok * NC + it) * CS + tt]);  // both threads of the row
+    if (has_k && tok_valid && tt < 16)  // both threads of the row
+      eta_i = __bfloat162float(p.last_eta[((size_t)bh_tok * p.NC + (kTraj ? p.t0 : 0) + it) * CS + tt]);
+    if (kTraj) {  // image of the state before this step (slot it; the last pass, it == nsteps, saves the final state)
+      p.b1img[((size_t)blockIdx.x * p.img_slots + it) * 128 + tid] = b1r;
+      if (tid == 0) {
+        bulk_store_1d(p.img + ((size_t)blockIdx.x * p.img_slots + it) * 16384, smem + SM_W1B, 16384);
+        bulk_commit();
+      }
+      if (!has_k) break;
+    }
 
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
     if (tid == 0 && it < NC) issue_loads(it + 1, slot ^ 1);
@@ -261,6 +278,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
     // ---- MMA-U: W1^T += G^T . K   (A MN-major: 32 token rows x 2 blocks of 64 f_out; B = K rows of the token tile)
     if (tid == 0) {
+      if (kTraj) bulk_wait_read<0>();  // the image store must have read W1b before the epilogue below rewrites it
       tc_fence_after();
       const uint64_t da = make_desc_sw128(sbase + SM_GT, 4096, 1024);
       const uint64_t db = make_desc_sw128(tok, 1024, 1024);
@@ -280,8 +298,8 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc_fence_after();
     {
       const int nstep = it + 1;
-      const bool ck = p.W1c && row_valid && nstep < NC && (nstep % p.ckpt_group == 0);
-      const bool fin = p.W1o && row_valid && nstep == NC;
+      const bool ck = !kTraj && p.W1c && row_valid && nstep < NC && (nstep % p.ckpt_group == 0);
+      const bool fin = !kTraj && p.W1o && row_valid && nstep == NC;
       const size_t kidx = ck ? ((size_t)bh_row * p.K + nstep / p.ckpt_group) : 0;
       uint32_t v[32];
 #pragma unroll
@@ -310,6 +328,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncthreads();
   }
 
+  if (kTraj && tid == 0) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<128>(tmem);
@@ -332,13 +351,39 @@ cudaError_t launch_linear_forward(const void* XQ, const void* XK, const void* XV
   p.ln_w = ln_w; p.ln_b = ln_b; p.W1 = W1; p.b1 = b1; p.W1c = W1c; p.b1c = b1c; p.W1o = W1o; p.b1o = b1o;
   p.Out = reinterpret_cast<__nv_bfloat16*>(Out);
   p.BH = B * H; p.H = H; p.NC = NC; p.ckpt_group = ckpt_group; p.K = (NC + ckpt_group - 1) / ckpt_group;
+  p.w_stride = lin::F * lin::F; p.b_stride = lin::F;
   static bool attr_done = false;
   if (!attr_done) {
-    TB_TRY(cudaFuncSetAttribute(lin::ttt_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SM_TOTAL), "smem attr");
+    TB_TRY(cudaFuncSetAttribute(lin::ttt_linear_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SM_TOTAL), "smem attr");
     attr_done = true;
   }
   g_where = "linear forward launch";
-  lin::ttt_linear_fwd_kernel<<<(p.BH + 1) / 2, lin::NT, lin::SM_TOTAL, stream>>>(tq, tk, tv, p);
+  lin::ttt_linear_fwd_kernel<false><<<(p.BH + 1) / 2, lin::NT, lin::SM_TOTAL, stream>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+
+// Backward recompute: steps t0 .. t0+nsteps-1 from the checkpointed state (W1s + bh*w_stride, b1s + bh*b_stride), saving
+// nsteps+1 operand images (see LinParams).  Used by launch_linear_backward (ttt_linear_bwd.cu).
+cudaError_t launch_linear_trajectory(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
+                                     const float* ln_b, const float* W1s, const float* b1s, long long w_stride,
+                                     long long b_stride, uint8_t* img, float* b1img, int img_slots, int B, int H, int NC,
+                                     int t0, int nsteps, cudaStream_t stream) {
+  if (nsteps <= 0 || nsteps + 1 > img_slots || t0 < 0 || t0 + nsteps > NC) { g_where = "bad trajectory window"; return cudaErrorInvalidValue; }
+  const uint64_t rows = (uint64_t)B * H * NC * lin::CS;
+  CUtensorMap tk, tv;
+  if (make_token_tmap_box(&tk, XK, rows, 16) || make_token_tmap_box(&tv, XV, rows, 16)) return cudaErrorInvalidValue;
+  lin::LinParams p{};
+  p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
+  p.ln_w = ln_w; p.ln_b = ln_b; p.W1 = W1s; p.b1 = b1s; p.w_stride = w_stride; p.b_stride = b_stride;
+  p.BH = B * H; p.H = H; p.NC = NC; p.ckpt_group = 1; p.K = 1;
+  p.t0 = t0; p.nsteps = nsteps; p.img_slots = img_slots; p.img = img; p.b1img = b1img;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TB_TRY(cudaFuncSetAttribute(lin::ttt_linear_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SM_TOTAL), "smem attr");
+    attr_done = true;
+  }
+  g_where = "linear trajectory launch";
+  lin::ttt_linear_fwd_kernel<true><<<(p.BH + 1) / 2, lin::NT, lin::SM_TOTAL, stream>>>(tk, tk, tv, p);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "bwd_common.cuh"
 #include "ptx.cuh"
@@ -61,6 +62,7 @@ struct BwdParams {
   int t_hi, t_lo, t0;  // iterations t_hi..t_lo (descending); image slot of W_t is t - t0
   int first;           // 1: start from zero state gradient, 0: load it from the scratch
   unsigned* dbg;       // phase-timing buffer (debug builds)
+  int dbg_group;       // group (t_lo / G) whose observer phase times are dumped
 };
 
 __global__ void __launch_bounds__(NT, 1)
@@ -74,6 +76,11 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   const int j = tid;
   TICK_DECL(22, 224)
+#ifdef TTT_PHASE_TIMING
+  const long long tick_t0_64 = clock64();
+  unsigned long long tick_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tick_g0));
+#endif
 
   float* lnw = reinterpret_cast<float*>(smem + SM_MISC);  // [64]
   float* lnb = lnw + 64;
@@ -610,7 +617,22 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   }
   TICK(16);  // epilogue stores
-  TICK_DUMP(22, p.dbg);
+  if (p.t_lo / p.G == p.dbg_group) TICK_DUMP(22, p.dbg);
+#ifdef TTT_PHASE_TIMING
+  if (p.dbg && tid == 0 && blockIdx.x < 64) {  // per-block total cycles + SM id (placement effects)
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.dbg[128 + blockIdx.x] = (unsigned)(clock64() - tick_t0_64);
+    p.dbg[192 + blockIdx.x] = smid;
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    const int gi = p.t_lo / p.G;  // block start / end wall time (ns, low 32 bits), one record per group (up to 27)
+    if (gi < 27) {
+      p.dbg[512 + gi * 128 + blockIdx.x] = (unsigned)tick_g0;
+      p.dbg[512 + gi * 128 + 64 + blockIdx.x] = (unsigned)g1;
+    }
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -730,7 +752,8 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.t_hi = t1 - 1;
     p.t_lo = t0; p.t0 = t0;
     p.first = last ? 1 : 0;
-    p.dbg = (g == 0) ? g_timing_buf : nullptr;  // time the last launch (a full group)
+    { const char* dg = getenv("TTT_DBG_GROUP"); p.dbg_group = dg ? atoi(dg) : 0; }
+    p.dbg = g_timing_buf;  // observers: the last launch (g == 0, a full group) wins; per-group stamps are kept
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
     if (g >= kRing) {  // ring buffer r is free again once this launch is done: recompute group g - kRing into it

@@ -3,9 +3,8 @@ libttt_b200.so -- hand-written sm_100a CUDA, no Triton.
 
 ``TritonLinear.apply(ttt_norm_weight, ttt_norm_bias, W1_init, b1_init, XQ, XV, XK, eta, checkpoint_group_size)`` keeps
 the reference's signature (Q, V, K order, linear_triton.py:16-27) and the saved checkpoints (W1/b1 every
-``checkpoint_group_size`` mini-batches, linear_triton.py:87-88).  Round-1 state: the forward scan is native; the
-backward scan kernel (reference: kernels/linear_backward.py) is not built yet, so calling ``.backward`` raises -- there
-is deliberately no eager fallback.
+``checkpoint_group_size`` mini-batches, linear_triton.py:87-88).  Forward and backward scans are both native
+(csrc/ttt_linear_fwd.cu, csrc/ttt_linear_bwd.cu); there is deliberately no eager fallback.
 """
 import math
 
@@ -43,6 +42,35 @@ def linear_forward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, checkpoint_group_si
     return out, (W1c, b1c), ((W1l, b1l) if want_last else None)
 
 
+def linear_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1c, b1c, dOut, checkpoint_group_size):
+    """Native TTT-Linear backward (reference: linear_triton.py:148-265).  Tensors as in linear_forward; dOut bf16
+    [B,H,NC,16,64].  Returns (d ln_w [H,64], d ln_b [H,64], dW1 [B,H,64,64], db1 [B,H,1,64], dXQ, dXV, dXK (bf16),
+    d last_eta f32 [B,H,NC,16])."""
+    B, H, NC, CS, F = XQ.shape
+    dev = XQ.device
+    G = min(int(checkpoint_group_size), NC)
+    le = last_eta.to(torch.bfloat16).reshape(B, H, NC, CS).contiguous()
+    lw = ln_w.detach().reshape(H, F).float().contiguous()
+    lb = ln_b.detach().reshape(H, F).float().contiguous()
+    go = dOut.to(torch.bfloat16).contiguous()
+    f32 = dict(device=dev, dtype=torch.float32)
+    dlw = torch.empty(B, H, F, **f32)
+    dlb = torch.empty(B, H, F, **f32)
+    dW1 = torch.empty(B, H, F, F, **f32)
+    db1 = torch.empty(B, H, 1, F, **f32)
+    de = torch.empty(B, H, NC, CS, **f32)
+    dq, dk, dv = torch.empty_like(XQ), torch.empty_like(XK), torch.empty_like(XV)
+    L = _lib.lib()
+    nbytes = L.ttt_b200_linear_backward_workspace_bytes(B, H, NC, G)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    p = _lib.ptr
+    code = L.ttt_b200_linear_backward(p(XQ), p(XK), p(XV), p(le), p(lw), p(lb), p(W1c), p(b1c), p(go), p(dlw), p(dlb),
+                                      p(dW1), p(db1), p(de), p(dq), p(dk), p(dv), p(ws), nbytes, B, H, NC, G,
+                                      _lib.current_stream())
+    _lib.check(code, "ttt_b200_linear_backward")
+    return dlw.sum(0), dlb.sum(0), dW1, db1, dq, dv, dk, de
+
+
 class TritonLinear(torch.autograd.Function):
     """Same name / call signature as the reference's TritonLinear (linear_triton.py:12)."""
 
@@ -57,8 +85,20 @@ class TritonLinear(torch.autograd.Function):
         out, ck, _ = linear_forward(XQ_batch.to(bf).contiguous(), XK_batch.to(bf).contiguous(), XV_batch.to(bf).contiguous(),
                                     last_eta, ttt_norm_weight, ttt_norm_bias, W1_init, b1_init, checkpoint_group_size)
         ctx.save_for_backward(XQ_batch, XV_batch, XK_batch, last_eta, ttt_norm_weight, ttt_norm_bias, *ck)
+        ctx.group = int(checkpoint_group_size)
+        ctx.eta_shape = eta_batch.shape
         return out.to(mp)
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise RuntimeError("ttt_b200: the TTT-Linear backward kernel is not built in this round (no eager fallback by design)")
+        XQ, XV, XK, last_eta, ln_w, ln_b, W1c, b1c = ctx.saved_tensors
+        mp = XQ.dtype
+        bf = torch.bfloat16
+        dlw, dlb, dW1, db1, dq, dv, dk, de = linear_backward(XQ.to(bf).contiguous(), XK.to(bf).contiguous(),
+                                                             XV.to(bf).contiguous(), last_eta, ln_w, ln_b, W1c, b1c,
+                                                             grad_out, ctx.group)
+        # the scan reads only the last eta row (kernels/linear_forward.py:90-101): the other rows get zero gradient
+        d_eta = torch.zeros(ctx.eta_shape, device=XQ.device, dtype=mp)
+        d_eta[:, :, :, -1, :] = de.to(mp)
+        return (dlw.reshape(ln_w.shape).to(ln_w.dtype), dlb.reshape(ln_b.shape).to(ln_b.dtype), dW1.to(mp), db1.to(mp),
+                dq.to(mp), dv.to(mp), dk.to(mp), d_eta, None)
