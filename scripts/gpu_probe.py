@@ -48,7 +48,7 @@ import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import _lib, mlp_tk
-buf = torch.zeros(4096, dtype=torch.int32, device='cuda')
+buf = torch.zeros(8192, dtype=torch.int32, device='cuda')
 print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
 B,H,NC,G = 1,48,int(os.environ.get('TTT_TIMING_NC','64')),16
 d = O.make_inputs(B,H,NC,seed=1)
@@ -84,6 +84,8 @@ for rep in range(2):
             if base is None: base = min(st)
             ss = sorted((x-base)/1e3 for x in st); ee = sorted((x-base)/1e3 for x in en)
             print('group %%2d: first start %%8.1f last start %%8.1f | first end %%8.1f last end %%8.1f  (us)' %% (gi, ss[0], ss[-1], ee[0], ee[-1]), flush=True)
+            sts = [x & 0xffffffff for x in t[4096+gi*32:4096+gi*32+16]]
+            print('          step durations us (t_hi..t_lo):', [round(((sts[k-1]-sts[k]) & 0xffffffff)/1e3,1) for k in range(15,0,-1) if sts[k] and sts[k-1]], flush=True)
     buf.zero_()
 """ % (ROOT, ROOT, ROOT),
     "timeline": """
@@ -145,6 +147,50 @@ for rep in range(3):
     torch.cuda.synchronize(); t2=time.time()
     print('linear NC=1128 B=1: fwd %%.3f ms  bwd %%.3f ms' %% ((t1-t0)*1e3, (t2-t1)*1e3), flush=True)
 """ % (ROOT, ROOT),
+    "lin_steps": """
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+import test_gpu_linear_backward as T
+for NC in (4, 6, 9):
+    B,H,G = 1,1,1000
+    d = O.make_inputs(B,H,NC,CS=16,seed=70+NC,base_lr=1.0,linear=True)
+    out, g = T.run_fwd_bwd(d, G)
+    r = lambda t: t.to(torch.bfloat16).float()
+    le = r(d['eta'])[:,:,:,-1,:].unsqueeze(-1)
+    ref = O.ttt_linear_primal_backward(r(d['XQ']), r(d['XK']), r(d['XV']), le, d['ln_w'], d['ln_b'], d['W1'], d['b1'], r(d['dOut']))
+    for n, a, b in (('dXV', g[5], ref['dXV']), ('dXK', g[6], ref['dXK']), ('dXQ-dO', g[4].float().cpu() - r(d['dOut']), ref['dXQ'] - r(d['dOut'])), ('dEta', g[7][:,:,:,-1,:], ref['dlast_eta'].squeeze(-1))):
+        a = a.float().cpu()
+        print('NC', NC, n, 'per-step rel err', [float('%%.2e' %% O.rel_err(a[:,:,t], b[:,:,t])) for t in range(NC)], flush=True)
+    print('NC', NC, 'dW1', O.rel_err(g[2].float().cpu(), ref['dW1']), 'db1', O.rel_err(g[3].float().cpu(), ref['db1']), flush=True)
+""" % (ROOT, ROOT),
+    "lin_timing": """
+import os
+os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from ttt_video_dit_b200 import _lib, linear_triton
+buf = torch.zeros(8192, dtype=torch.int32, device='cuda')
+print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
+B,H,NC,G = 1,48,256,16
+d = O.make_inputs(B,H,NC,CS=16,seed=1,base_lr=1.0,linear=True)
+dev='cuda'; bf = lambda t: t.to(torch.bfloat16).to(dev)
+prm = [d[k].to(dev).requires_grad_(True) for k in ('ln_w','ln_b','W1','b1')]
+q,v,k,e = [bf(d[n]).requires_grad_(True) for n in ('XQ','XV','XK','eta')]
+go = bf(d['dOut'])
+for rep in range(2):
+    out = linear_triton.TritonLinear.apply(*prm, q, v, k, e, G)
+    buf.zero_()
+    out.backward(go)
+    torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    kn = ['waits K/img/Z','TP1','wait upd','cvt','issue C','D epilogue','wait dG','TP2','issue F']
+    qn = ['waits Q/img','Zq mma','TPq','slot+tile','dQ mma','dQ store']
+    if rep == 1:
+        print('K group cycles/step total', sum(t[0:9])/NC, {n: round(t[i]/NC) for i,n in enumerate(kn)}, flush=True)
+        print('Q group cycles/step total', sum(t[64:70])/NC, {n: round(t[64+i]/NC) for i,n in enumerate(qn)}, flush=True)
+""" % (ROOT, ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

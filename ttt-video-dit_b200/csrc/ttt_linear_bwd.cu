@@ -45,8 +45,8 @@ constexpr uint32_t SM_DZQ = SM_DZ + 16384;         // 2 x dZ1bar tile           
 constexpr uint32_t SM_V = SM_DZQ + 2 * 16384;      // 3 x V tile [16][64]                                          6 KB
 constexpr uint32_t SM_DO = SM_V + 3 * 2048;        // 3 x dOut tile [16][64]                                       6 KB
 constexpr uint32_t SM_MISC = SM_DO + 3 * 2048;
-constexpr uint32_t MISC_BARS = 6656;
-constexpr uint32_t SM_TOTAL = SM_MISC + 7168;
+constexpr uint32_t MISC_BARS = 7680;
+constexpr uint32_t SM_TOTAL = SM_MISC + 8192;
 
 constexpr uint32_t TM_DW = 0, TM_DZ = 64, TM_DG = 128, TM_DK0 = 192, TM_DK1 = 256, TM_DZQ = 320, TM_DQ = 384;
 
@@ -62,6 +62,7 @@ struct LinBwdParams {
   int H, NC, img_slots;
   int t_hi, t_lo, t0;             // steps t_hi .. t_lo (descending); image of the state before step u = slot u - t0
   int first;                      // 1: start from a zero state gradient, 0: load it from dW1 / db1
+  unsigned* dbg;                  // phase-timing buffer (debug builds)
 };
 
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
@@ -126,10 +127,12 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int NC = p.NC;
   const int nst = p.t_hi - p.t_lo + 1;
   const uint32_t lane_addr = ((uint32_t)(gw * 32)) << 16;
+  TICK_DECL(12, 128)
 
   float* fm = reinterpret_cast<float*>(smem + SM_MISC);
   float* b1s = fm;          // [4][64] b1 of the image ring
-  float* qdb1 = fm + 256;   // [2][64] column sums of dZ1bar (Q group -> K group)
+  float* qdb1 = fm + 1664;  // [4][64] column sums of dZ1bar (Q group -> K group; read by the K group AFTER the factor
+                            // tile of the same step was consumed, so it needs its own, deeper ring)
   float* db1c = fm + 384;   // [64] carried d b1
   float* db1n = fm + 448;   // [64] d b1 after this step's Q side
   float* lnw = fm + 512;
@@ -243,6 +246,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(&bar_img[t & 3], ((i + 1) >> 2) & 1);
       mbar_wait(bar_mz, i & 1);
       tc_fence_after();
+      TICK(0);  // loop tail + waits for K/V, image, Z1 MMA
       float xh[16], gxh[16], go[16], gz[16];
       float rstd, s2c;
       {
@@ -285,9 +289,11 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (act) st_tok4(gt, j, 2 * gw, gv);
       }
 
+      TICK(1);  // first-order pass
       // ---- (B) carried d W1^T (complete once last step's update and this step's Q-side factor landed) -> bf16 image
       mbar_wait(bar_upd, i & 1);
       tc_fence_after();
+      TICK(2);  // wait for the state gradient
       {
         const int row = tid & 63, half = tid >> 6;
         uint32_t v[32];
@@ -301,11 +307,12 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                        pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
                        pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
       }
-      if (tid < 64) db1n[tid] = db1c[tid] + qdb1[(i & 1) * 64 + tid];
+      if (tid < 64) db1n[tid] = db1c[tid] + qdb1[(i & 3) * 64 + tid];
       fence_proxy_async();
       tc_fence_before();
       group_sync(1);
 
+      TICK(3);  // accumulator -> bf16 image
       // ---- (C) dG = K . dW1' ; dK = G . dW1'^T ; then the next step's Z1 recompute
       if (tid == 0) {
         tc_fence_after();
@@ -320,6 +327,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
 
+      TICK(4);  // MMA issue
       // ---- (D) deferred epilogue of the previous step: d XK, then refill the buffers it released
       if (i > 0) {
         mbar_wait(bar_mkb, (i - 1) & 1);
@@ -339,9 +347,11 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
 
+      TICK(5);  // deferred d XK epilogue + refills
       // ---- (E) second-order pass: backward through gradZ1 = ln_fused_l2_bwd(Z1, V - K)
       mbar_wait(bar_mg, i & 1);
       tc_fence_after();
+      TICK(6);  // wait for dG
       {
         uint32_t r[16];
         tmem_ld16(tmem + lane_addr + TM_DG + c0, r);
@@ -394,6 +404,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       group_sync(1);
 
+      TICK(7);  // second-order pass
       // ---- (F) dK += dZ1 . W1^T ; dW^T += dZ1^T . K ; then fold the next step's Q-side factor
       if (tid == 0) {
         tc_fence_after();
@@ -408,6 +419,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
       eta_c = eta_n;
+      TICK(8);  // MMA issue (+ wait for the Q-side factor)
     }
 
     // ---- epilogue of the last step + carried state gradient -> global
@@ -464,6 +476,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
       mbar_wait(&bar_q[qs3], (i / 3) & 1);
       mbar_wait(&bar_img[(t + 1) & 3], (i >> 2) & 1);
+      TICK(0);  // waits for Q/dOut, image
       if (tid == 128) {
         tc_fence_after();
         mma_kk(tmem + TM_DZQ, qt, img_n);  // Z1bar = Q . W1'
@@ -472,6 +485,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(bar_mq, mq_phase);
       mq_phase ^= 1;
       tc_fence_after();
+      TICK(1);  // Z1bar MMA
       float dov[16];
       {
         uint32_t r[16];
@@ -507,6 +521,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         float dz[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) dz[e] = (fmaf(64.f, dxh[e], -sq[0]) - z[e] * sq[1]) * sc;
+        TICK(2);  // output-LN backward
         if (i >= 2) {  // factor-tile slot: the K group must have folded step i-2 (same slot) into the state gradient
           mbar_wait(&bar_qfree[ds], ((i >> 1) - 1) & 1);
           if (tid == 128 && i + 1 < nst) load_q(i + 1);  // ... which also released the Q / dOut slot of step i-2
@@ -518,11 +533,12 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (int e = 0; e < 16; ++e) dz[e] = 0.f;
         }
         warp_colsum16(dz, lane);
-        if ((lane & 1) == 0) qdb1[ds * 64 + c0 + (lane >> 1)] = dz[0];
+        if ((lane & 1) == 0) qdb1[(i & 3) * 64 + c0 + (lane >> 1)] = dz[0];
       }
       fence_proxy_async();
       tc_fence_before();
       group_sync(2);
+      TICK(3);  // wait for the slot + tile write
       if (tid == 128) {
         mbar_arrive(&bar_qready[ds]);
         tc_fence_after();
@@ -532,6 +548,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(bar_mq, mq_phase);
       mq_phase ^= 1;
       tc_fence_after();
+      TICK(4);  // dQ MMA
       {
         uint32_t r[16];
         tmem_ld16(tmem + lane_addr + TM_DQ + c0, r);
@@ -545,6 +562,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       tc_fence_before();
       group_sync(2);
+      TICK(5);  // d XQ store
     }
     if (!act) {
 #pragma unroll
@@ -558,6 +576,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   }
 
+  TICK_DUMP(12, p.dbg);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -650,6 +669,7 @@ cudaError_t launch_linear_backward(const void* XQ, const void* XK, const void* X
     p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
     p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = dEta; p.dlnw = dlnw; p.dlnb = dlnb;
     p.H = H; p.NC = NC; p.img_slots = (int)slots; p.t_hi = t0 + n - 1; p.t_lo = t0; p.t0 = t0; p.first = (w == nwin - 1);
+    p.dbg = g_timing_buf;
     g_where = "linear backward launch";
     linb::ttt_linear_bwd_kernel<<<BH, linb::NT, linb::SM_TOTAL, stream>>>(tq, tk, tv, tdo, p);
     TB_TRY(cudaGetLastError(), "linear backward launch");

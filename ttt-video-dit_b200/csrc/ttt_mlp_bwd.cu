@@ -229,6 +229,13 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
     __syncthreads();  // b2t / etas visible
       TICK(0);
+#ifdef TTT_PHASE_TIMING
+    if (p.dbg && tid == 0 && blockIdx.x == 0 && p.t_lo / p.G < 27) {  // wall-clock stamp of every step (block 0)
+      unsigned long long gs;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gs));
+      p.dbg[4096 + (p.t_lo / p.G) * 32 + (t - p.t_lo)] = (unsigned)gs;
+    }
+#endif
 
     if (has_k) {
       // ===== A1 MMA: R1 = W1 . K^T -> (S0,S1)
