@@ -56,6 +56,20 @@ def bench_linear(NC=1128, H=48, B=1):
     flop = 3 * 2 * 16 * 64 * 64 * NC * H * B
     print(json.dumps({"kernel": "ttt_linear_fwd_kernel", "shape": [B, H, NC, 16, 64], "ms": ms, "tokens_per_s": B * NC * 16 / ms * 1e3,
                       "tflops": flop / ms / 1e9, "us_per_minibatch": ms * 1e3 / NC}))
+    # forward + backward through the TritonLinear mirror (trajectory recompute + reverse scan), checkpoint group 16
+    eta = le.float()[:, :, :, None, :].expand(B, H, NC, 16, 16).to(torch.bfloat16).contiguous()
+    prm = [t.clone().requires_grad_(True) for t in (lw, lb, W1, b1)]
+    qq, vv, kk, ee = [t.clone().requires_grad_(True) for t in (q, v, k, eta)]
+    go = r(B, H, NC, 16, 64).to(torch.bfloat16).to(dev)
+
+    def step():
+        out = linear_triton.TritonLinear.apply(*prm, qq, vv, kk, ee, 16)
+        out.backward(go)
+
+    ms2 = timeit(step)
+    flop2 = 9 * 2 * 16 * 64 * 64 * NC * H * B  # fwd 3 U_L + bwd 6 U_L; recompute not counted
+    print(json.dumps({"kernel": "ttt_linear fwd+bwd (TritonLinear.apply + backward)", "shape": [B, H, NC, 16, 64], "ms": ms2,
+                      "tokens_per_s": B * NC * 16 / ms2 * 1e3, "tflops": flop2 / ms2 / 1e9, "us_per_minibatch": ms2 * 1e3 / NC}))
 
 
 def bench_gate(L=18048, E=3072, B=1):

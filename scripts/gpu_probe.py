@@ -191,6 +191,40 @@ for rep in range(2):
         print('K group cycles/step total', sum(t[0:9])/NC, {n: round(t[i]/NC) for i,n in enumerate(kn)}, flush=True)
         print('Q group cycles/step total', sum(t[64:70])/NC, {n: round(t[64+i]/NC) for i,n in enumerate(qn)}, flush=True)
 """ % (ROOT, ROOT, ROOT),
+    "spin": """
+import os
+os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+import torch, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from ttt_video_dit_b200 import _lib, mlp_tk
+buf = torch.zeros(8192, dtype=torch.int32, device='cuda')
+sink = torch.zeros(128*1024*1024, dtype=torch.float32, device='cuda')  # 512 MB > L2
+print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
+B,H,NC,G = 1,48,32,16
+d = O.make_inputs(B,H,NC,seed=1)
+bf = lambda t: t.to(torch.bfloat16).cuda()
+prm = [d[k].cuda().requires_grad_(True) for k in ('ln_w','ln_b','W1','b1','W2','b2')]
+q,v,k = [bf(d[n]).requires_grad_(True) for n in ('XQ','XV','XK')]
+e = bf(d['eta'])[:,:,:,-1,:].clone().requires_grad_(True)
+go = bf(d['dOut'])
+side = torch.cuda.Stream()
+for label, mode, blocks, threads, smem in [('code28K 100x256', 9, 100, 256, 200*1024), ('code30K 100x256', 10, 100, 256, 200*1024), ('code32K 100x256', 11, 100, 256, 200*1024),
+                                           ('code36K 100x256', 12, 100, 256, 200*1024), ('code24K 100x256', 6, 100, 256, 200*1024), ('none', -1, 0, 0, 0)]:
+    for rep in range(2):
+        out = mlp_tk.ttt_mlp_op(*prm, q, v, k, e, G)
+        torch.cuda.synchronize()
+        buf.zero_()
+        if mode >= 0:
+            rc = _lib.lib().ttt_b200_debug_spin(blocks, threads, 6000000, mode, smem, _lib.ptr(sink), sink.numel(), side.cuda_stream)
+            assert rc == 0, rc
+        out.backward(go)
+        torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    for gi in (1, 0):
+        sts = [x & 0xffffffff for x in t[4096+gi*32:4096+gi*32+16]]
+        print('%%-14s group %%d step us:' %% (label, gi), [round(((sts[kk-1]-sts[kk]) & 0xffffffff)/1e3,1) for kk in range(15,0,-1)], flush=True)
+""" % (ROOT, ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

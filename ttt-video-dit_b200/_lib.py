@@ -24,6 +24,7 @@ _SIGS = {
     "ttt_b200_gate_backward": ([_vp, _vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_debug_set_timing_buffer": ([_vp], ctypes.c_int),
     "ttt_b200_debug_umma": ([_i, _vp, _vp, _fp, _i, _i, _vp], ctypes.c_int),
+    "ttt_b200_debug_spin": ([_i, _i, ctypes.c_longlong, _i, _i, _fp, ctypes.c_longlong, _vp], ctypes.c_int),
 }
 
 

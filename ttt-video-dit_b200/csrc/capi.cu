@@ -178,4 +178,16 @@ int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N
   return cuda_ret(tb::launch_umma_selftest(mode, A, Bm, D, N, K, (cudaStream_t)stream), "ttt_b200_debug_umma");
 }
 
+// Occupancy / interference experiments: `blocks` CTAs that spin for `cycles` SM cycles with a tiny code footprint and no
+// memory traffic.  mode 0: dependent FMA chains (ALU busy), mode 1: nanosleep (SM occupied but idle), mode 2 / 3:
+// streaming stores / loads over sink[0 .. sink_floats).  smem_bytes of dynamic shared memory pins one CTA per SM when
+// set close to the maximum.
+int ttt_b200_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
+                        long long sink_floats, void* stream) {
+  if (!sink) return fail(-1, "ttt_b200_debug_spin: null pointer argument");
+  if (int rc = bind_device(sink)) return rc;
+  return cuda_ret(tb::launch_debug_spin(blocks, threads, cycles, mode, smem_bytes, sink, sink_floats, (cudaStream_t)stream),
+                  "ttt_b200_debug_spin");
+}
+
 }  // extern "C"

@@ -84,3 +84,8 @@ cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo,
                                   float* qb2, void* dXQ, float* dlnw, float* dlnb, int BH, int H, int NC, int img_slots,
                                   int G, int t0, int nsteps, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
+                              long long sink_floats, cudaStream_t stream);
+}  // namespace tb

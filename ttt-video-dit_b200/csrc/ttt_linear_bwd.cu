@@ -13,9 +13,10 @@
 // row sums are exchanged between the 4 warps through shared memory + a named barrier.  Two warp groups:
 //   K group (warps 0-3): the sequential chain   dW' -> bf16 image -> dG = K.dW' , dK = G.dW'^T -> second-order LN
 //                         backward -> dZ1 -> dK += dZ1.W1^T , dW^T += dZ1^T.K
-//   Q group (warps 4-7): everything that does not depend on the carried gradient (Z1bar recompute, output-LN backward,
-//                         dQ, the dZ1bar^T.Q factor tile), running up to two steps ahead; the K-group leader folds the
-//                         factor into dW^T with one K=16 MMA.
+//   Q group (warps 4-5): everything that does not depend on the carried gradient (Z1bar recompute, output-LN backward,
+//                         dQ, the dZ1bar^T.Q factor tile), running up to two steps ahead.
+//   issue warp (warp 6):  one thread issues every K-side MMA, folds the Q-side factor into dW^T with one K=16 MMA and
+//                         refills the K / V / state-image buffers by TMA, so the compute warps never block on issue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,7 +34,7 @@ using bwd::st_global16;
 using bwd::st_row16;
 using bwd::warp_colsum16;
 
-constexpr int CS = 16, F = 64, NT = 256;
+constexpr int CS = 16, F = 64, NT = 224;  // 4 K-group warps + 2 Q-group warps + 1 MMA / TMA issue warp
 
 constexpr uint32_t SM_IMG = 0;                     // ring of 4 W1^T images (slot = step & 3), [64 f_out][64 f_in] K-major
 constexpr uint32_t SM_DWI = 32768;                 // bf16 image of the carried d W1^T                             8 KB
@@ -79,6 +80,19 @@ __device__ __forceinline__ void group_rowsum(float* xb, int gw, int j, bool act,
   for (int n = 0; n < NV; ++n) v[n] = (xb[j * 4 + n] + xb[(16 + j) * 4 + n]) + (xb[(32 + j) * 4 + n] + xb[(48 + j) * 4 + n]);
 }
 
+// the Q group is a pair of warps
+__device__ __forceinline__ void pair_sync() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+template <int NV>
+__device__ __forceinline__ void pair_rowsum(float* xb, int gw, int j, bool act, float* v) {
+  if (act) {
+#pragma unroll
+    for (int n = 0; n < NV; ++n) xb[(gw * 16 + j) * 4 + n] = v[n];
+  }
+  pair_sync();
+#pragma unroll
+  for (int n = 0; n < NV; ++n) v[n] = xb[j * 4 + n] + xb[(16 + j) * 4 + n];
+}
+
 // 16 fp32 -> bf16 -> the 4 copies of token row j (tile rows 32c + j), chunks chunk0, chunk0 + 1
 __device__ __forceinline__ void st_tok4(uint32_t tile, int j, int chunk0, const float* v) {
   const uint32_t a0 = pack_bf16(v[0], v[1]), a1 = pack_bf16(v[2], v[3]), a2 = pack_bf16(v[4], v[5]), a3 = pack_bf16(v[6], v[7]);
@@ -111,6 +125,8 @@ __device__ __forceinline__ void mma_upd(uint32_t d, uint32_t a_tile, uint32_t b_
   umma_ss(d, make_desc_sw128(a_tile, 0, 1024), make_desc_sw128(b_tile, 1024, 1024), idesc, 1);
 }
 
+// seven warps: no SM sub-partition hosts more than two, so every thread may use up to 255 registers (a ninth warp
+// would put three on one sub-partition and cap the kernel at 168)
 __global__ void __launch_bounds__(NT, 1)
 ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -118,7 +134,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = tid >> 7;   // 0 = K group, 1 = Q group
+  const int grp = tid >> 7;   // 0 = K group (warps 0-3); warps 4-5 = Q group, warp 6 = issue warp
   const int gw = warp & 3;    // warp within the group = TMEM lane quadrant = 16-column quarter
   const int j = lane & 15;    // token row
   const bool act = lane < 16;
@@ -150,10 +166,12 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bar_qready = bars + 14;  // [2] Q-side factor tile written
   uint64_t* bar_qfree = bars + 16;   // [2] Q-side factor tile consumed
   uint64_t* bar_mq = bars + 18;    // Q-group MMAs
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* bar_kb = bars + 19;    // K group -> issue warp: state-gradient image + G tile written (first: TMEM state loaded)
+  uint64_t* bar_ke = bars + 20;    // K group -> issue warp: dZ1 tile written
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
 
   if (tid == 0) {
-    for (int i = 0; i < 19; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 21; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
   }
@@ -195,11 +213,6 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   if (grp == 0) {
     // =============================================== K group ========================================================
-    if (tid == 0) {
-      for (int m = 0; m < 4; ++m)
-        if (p.t_hi + 1 - m >= p.t_lo) load_image(p.t_hi + 1 - m);
-      for (int i = 0; i < 3 && i < nst; ++i) load_k(i);
-    }
     {  // carried d W1^T -> TMEM (lanes 64-127 mirror lanes 0-63)
       const int row = tid & 63;
       const float* src = p.dW1 + (size_t)bh * F * F;
@@ -214,17 +227,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     tc_fence_before();
     group_sync(1);
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(&bar_qready[0], 0);  // fold the Q side of the first step, then release the chain
-      mma_upd(tmem + TM_DW, sbase + SM_DZQ, sbase + SM_QT);
-      tc_commit(bar_upd);
-      tc_commit(&bar_qfree[0]);
-      mbar_wait(&bar_k[0], 0);
-      mbar_wait(&bar_img[p.t_hi & 3], 0);
-      mma_kk(tmem + TM_DZ, sbase + SM_KT, sbase + SM_IMG + (p.t_hi & 3) * 8192);
-      tc_commit(bar_mz);
-    }
+    if (tid == 0) mbar_arrive(bar_kb);
 
     float eta_c = __bfloat162float(p.last_eta[((size_t)bh * NC + p.t_hi) * CS + j]);
     float dgam[16], dbet[16], dyp[16];
@@ -236,7 +239,6 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int t = p.t_hi - i;
       const int ks = i % 3;
       const uint32_t kt = sbase + SM_KT + ks * 16384, vt = sbase + SM_V + ks * 2048;
-      const uint32_t img_t = sbase + SM_IMG + (t & 3) * 8192;
       const uint32_t gt = sbase + SM_G, dzt = sbase + SM_DZ, dwi = sbase + SM_DWI;
       const float* b1t = b1s + (t & 3) * 64;
       const float eta_n = (i + 1 < nst) ? __bfloat162float(p.last_eta[((size_t)bh * NC + t - 1) * CS + j]) : 0.f;
@@ -313,19 +315,8 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       group_sync(1);
 
       TICK(3);  // accumulator -> bf16 image
-      // ---- (C) dG = K . dW1' ; dK = G . dW1'^T ; then the next step's Z1 recompute
-      if (tid == 0) {
-        tc_fence_after();
-        mma_kk(tmem + TM_DG, kt, dwi);
-        mma_kn(tmem + ((i & 1) ? TM_DK1 : TM_DK0), gt, dwi, false);
-        tc_commit(bar_mg);
-        if (i + 1 < nst) {
-          mbar_wait(&bar_k[(i + 1) % 3], ((i + 1) / 3) & 1);
-          mbar_wait(&bar_img[(t - 1) & 3], ((i + 2) >> 2) & 1);
-          mma_kk(tmem + TM_DZ, sbase + SM_KT + ((i + 1) % 3) * 16384, sbase + SM_IMG + ((t - 1) & 3) * 8192);
-          tc_commit(bar_mz);
-        }
-      }
+      // ---- (C) issue warp: dG = K . dW1' ; dK = G . dW1'^T ; then the next step's Z1 recompute
+      if (tid == 0) mbar_arrive(bar_kb);
 
       TICK(4);  // MMA issue
       // ---- (D) deferred epilogue of the previous step: d XK, then refill the buffers it released
@@ -340,10 +331,6 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]) + dyp[e];
           st_global16(p.dXK + (((size_t)bh * NC + t + 1) * CS + j) * F + c0, o);
-        }
-        if (tid == 0) {
-          if (i + 2 < nst) load_k(i + 2);
-          if (t - 2 >= p.t_lo) load_image(t - 2);
         }
       }
 
@@ -405,19 +392,8 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       group_sync(1);
 
       TICK(7);  // second-order pass
-      // ---- (F) dK += dZ1 . W1^T ; dW^T += dZ1^T . K ; then fold the next step's Q-side factor
-      if (tid == 0) {
-        tc_fence_after();
-        mma_kn(tmem + ((i & 1) ? TM_DK1 : TM_DK0), dzt, img_t, true);
-        mma_upd(tmem + TM_DW, dzt, kt);
-        tc_commit(bar_mkb);
-        if (i + 1 < nst) {
-          mbar_wait(&bar_qready[(i + 1) & 1], ((i + 1) >> 1) & 1);
-          mma_upd(tmem + TM_DW, sbase + SM_DZQ + ((i + 1) & 1) * 16384, sbase + SM_QT + ((i + 1) % 3) * 16384);
-          tc_commit(bar_upd);
-          tc_commit(&bar_qfree[(i + 1) & 1]);
-        }
-      }
+      // ---- (F) issue warp: dK += dZ1 . W1^T ; dW^T += dZ1^T . K ; then fold the next step's Q-side factor
+      if (tid == 0) mbar_arrive(bar_ke);
       eta_c = eta_n;
       TICK(8);  // MMA issue (+ wait for the Q-side factor)
     }
@@ -457,13 +433,16 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       atomicAdd(p.dlnw + (size_t)bh * F + c0 + (lane >> 1), dgam[0]);
       atomicAdd(p.dlnb + (size_t)bh * F + c0 + (lane >> 1), dbet[0]);
     }
-  } else {
+  } else if (warp < 6) {
     // =============================================== Q group ========================================================
+    // two warps (TMEM lane quadrants 0 and 1), each thread = one token x 32 columns: this group has slack, and seven
+    // warps in total keep every SM sub-partition at two warps, i.e. the full 255-register budget for the K group
+    const int q0 = 32 * gw;  // first column of this thread
     if (tid == 128)
       for (int i = 0; i < 3 && i < nst; ++i) load_q(i);
-    float dgq[16], dbq[16];
+    float dgq[32], dbq[32];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { dgq[e] = 0.f; dbq[e] = 0.f; }
+    for (int e = 0; e < 32; ++e) { dgq[e] = 0.f; dbq[e] = 0.f; }
     uint32_t mq_phase = 0;
     int xsel = 0;
     for (int i = 0; i < nst; ++i) {
@@ -486,58 +465,63 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mq_phase ^= 1;
       tc_fence_after();
       TICK(1);  // Z1bar MMA
-      float dov[16];
+      float dov[32];
       {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_addr + TM_DZQ + c0, r);
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_addr + TM_DZQ + q0, r);
         tc_wait_ld();
-        float z[16], ex[2] = {0.f, 0.f};
+        float z[32], ex[2] = {0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          z[e] = __uint_as_float(r[e]) + b1n[c0 + e];
+        for (int e = 0; e < 32; ++e) {
+          z[e] = __uint_as_float(r[e]) + b1n[q0 + e];
           ex[0] += z[e];
           ex[1] = fmaf(z[e], z[e], ex[1]);
         }
-        group_rowsum<2>(xq + xsel * 256, gw, j, act, 2, ex);
+        pair_rowsum<2>(xq + xsel * 256, gw, j, act, ex);
         xsel ^= 1;
         const float mu = ex[0] * (1.f / 64.f);
         const float rstd = rsqrtf(fmaxf(ex[1] * (1.f / 64.f) - mu * mu, 0.f) + 1e-8f);
-        ld_row16(dot, j, 2 * gw, dov);
-        float dxh[16], sq[2] = {0.f, 0.f};
+        ld_row16(dot, j, 4 * gw, dov);
+        ld_row16(dot, j, 4 * gw + 2, dov + 16);
+        float sq[2] = {0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 32; ++e) {
           z[e] = (z[e] - mu) * rstd;  // x_hat of the output LayerNorm
-          dxh[e] = dov[e] * lnw[c0 + e];
-          sq[0] += dxh[e];
-          sq[1] = fmaf(dxh[e], z[e], sq[1]);
+          const float dxh = dov[e] * lnw[q0 + e];
+          sq[0] += dxh;
+          sq[1] = fmaf(dxh, z[e], sq[1]);
           if (act) {
             dgq[e] = fmaf(dov[e], z[e], dgq[e]);
             dbq[e] += dov[e];
           }
         }
-        group_rowsum<2>(xq + xsel * 256, gw, j, act, 2, sq);
+        pair_rowsum<2>(xq + xsel * 256, gw, j, act, sq);
         xsel ^= 1;
         const float sc = rstd * (1.f / 64.f);
-        float dz[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dz[e] = (fmaf(64.f, dxh[e], -sq[0]) - z[e] * sq[1]) * sc;
+        for (int e = 0; e < 32; ++e) z[e] = (fmaf(64.f, dov[e] * lnw[q0 + e], -sq[0]) - z[e] * sq[1]) * sc;  // dZ1bar
         TICK(2);  // output-LN backward
-        if (i >= 2) {  // factor-tile slot: the K group must have folded step i-2 (same slot) into the state gradient
+        if (i >= 2) {  // factor-tile slot: the K side must have folded step i-2 (same slot) into the state gradient
           mbar_wait(&bar_qfree[ds], ((i >> 1) - 1) & 1);
           if (tid == 128 && i + 1 < nst) load_q(i + 1);  // ... which also released the Q / dOut slot of step i-2
         }
         if (act) {
-          st_tok4(dzq, j, 2 * gw, dz);
+          st_tok4(dzq, j, 4 * gw, z);
+          st_tok4(dzq, j, 4 * gw + 2, z + 16);
         } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) dz[e] = 0.f;
+          for (int e = 0; e < 32; ++e) z[e] = 0.f;
         }
-        warp_colsum16(dz, lane);
-        if ((lane & 1) == 0) qdb1[(i & 3) * 64 + c0 + (lane >> 1)] = dz[0];
+        warp_colsum16(z, lane);
+        warp_colsum16(z + 16, lane);
+        if ((lane & 1) == 0) {
+          qdb1[(i & 3) * 64 + q0 + (lane >> 1)] = z[0];
+          qdb1[(i & 3) * 64 + q0 + 16 + (lane >> 1)] = z[16];
+        }
       }
       fence_proxy_async();
       tc_fence_before();
-      group_sync(2);
+      pair_sync();
       TICK(3);  // wait for the slot + tile write
       if (tid == 128) {
         mbar_arrive(&bar_qready[ds]);
@@ -550,29 +534,87 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_after();
       TICK(4);  // dQ MMA
       {
-        uint32_t r[16];
-        tmem_ld16(tmem + lane_addr + TM_DQ + c0, r);
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_addr + TM_DQ + q0, r);
         tc_wait_ld();
         if (act) {
-          float o[16];
+          float o[32];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]) + dov[e];
-          st_global16(p.dXQ + (((size_t)bh * NC + t) * CS + j) * F + c0, o);
+          for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(r[e]) + dov[e];
+          __nv_bfloat16* dst = p.dXQ + (((size_t)bh * NC + t) * CS + j) * F + q0;
+          st_global16(dst, o);
+          st_global16(dst + 16, o + 16);
         }
       }
       tc_fence_before();
-      group_sync(2);
+      pair_sync();
       TICK(5);  // d XQ store
     }
     if (!act) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) { dgq[e] = 0.f; dbq[e] = 0.f; }
+      for (int e = 0; e < 32; ++e) { dgq[e] = 0.f; dbq[e] = 0.f; }
     }
     warp_colsum16(dgq, lane);
+    warp_colsum16(dgq + 16, lane);
     warp_colsum16(dbq, lane);
+    warp_colsum16(dbq + 16, lane);
     if ((lane & 1) == 0) {
-      atomicAdd(p.dlnw + (size_t)bh * F + c0 + (lane >> 1), dgq[0]);
-      atomicAdd(p.dlnb + (size_t)bh * F + c0 + (lane >> 1), dbq[0]);
+      atomicAdd(p.dlnw + (size_t)bh * F + q0 + (lane >> 1), dgq[0]);
+      atomicAdd(p.dlnw + (size_t)bh * F + q0 + 16 + (lane >> 1), dgq[16]);
+      atomicAdd(p.dlnb + (size_t)bh * F + q0 + (lane >> 1), dbq[0]);
+      atomicAdd(p.dlnb + (size_t)bh * F + q0 + 16 + (lane >> 1), dbq[16]);
+    }
+  }
+
+  else if (lane == 0) {
+    // =============================================== issue warp =====================================================
+    for (int m = 0; m < 4; ++m)
+      if (p.t_hi + 1 - m >= p.t_lo) load_image(p.t_hi + 1 - m);
+    for (int i = 0; i < 3 && i < nst; ++i) load_k(i);
+    const uint32_t gt = sbase + SM_G, dzt = sbase + SM_DZ, dwi = sbase + SM_DWI;
+    mbar_wait(bar_kb, 0);  // state gradient loaded into TMEM
+    tc_fence_after();
+    mbar_wait(&bar_qready[0], 0);  // fold the Q side of the first step, then release the chain
+    mma_upd(tmem + TM_DW, sbase + SM_DZQ, sbase + SM_QT);
+    tc_commit(bar_upd);
+    tc_commit(&bar_qfree[0]);
+    mbar_wait(&bar_k[0], 0);
+    mbar_wait(&bar_img[p.t_hi & 3], 0);
+    mma_kk(tmem + TM_DZ, sbase + SM_KT, sbase + SM_IMG + (p.t_hi & 3) * 8192);
+    tc_commit(bar_mz);
+    for (int i = 0; i < nst; ++i) {
+      const int t = p.t_hi - i;
+      const uint32_t kt = sbase + SM_KT + (i % 3) * 16384;
+      const uint32_t dk = tmem + ((i & 1) ? TM_DK1 : TM_DK0);
+      // (C) dG = K . dW1' ; dK = G . dW1'^T ; then the next step's Z1 recompute
+      mbar_wait(bar_kb, (i + 1) & 1);
+      tc_fence_after();
+      mma_kk(tmem + TM_DG, kt, dwi);
+      mma_kn(dk, gt, dwi, false);
+      tc_commit(bar_mg);
+      if (i + 1 < nst) {
+        mbar_wait(&bar_k[(i + 1) % 3], ((i + 1) / 3) & 1);
+        mbar_wait(&bar_img[(t - 1) & 3], ((i + 2) >> 2) & 1);
+        mma_kk(tmem + TM_DZ, sbase + SM_KT + ((i + 1) % 3) * 16384, sbase + SM_IMG + ((t - 1) & 3) * 8192);
+        tc_commit(bar_mz);
+      }
+      if (i > 0) {  // the previous step's update is complete: refill the K / V slot and the image slot it released
+        mbar_wait(bar_mkb, (i - 1) & 1);
+        if (i + 2 < nst) load_k(i + 2);
+        if (t - 2 >= p.t_lo) load_image(t - 2);
+      }
+      // (F) dK += dZ1 . W1^T ; dW^T += dZ1^T . K ; then fold the next step's Q-side factor
+      mbar_wait(bar_ke, i & 1);
+      tc_fence_after();
+      mma_kn(dk, dzt, sbase + SM_IMG + (t & 3) * 8192, true);
+      mma_upd(tmem + TM_DW, dzt, kt);
+      tc_commit(bar_mkb);
+      if (i + 1 < nst) {
+        mbar_wait(&bar_qready[(i + 1) & 1], ((i + 1) >> 1) & 1);
+        mma_upd(tmem + TM_DW, sbase + SM_DZQ + ((i + 1) & 1) * 16384, sbase + SM_QT + ((i + 1) % 3) * 16384);
+        tc_commit(bar_upd);
+        tc_commit(&bar_qfree[(i + 1) & 1]);
+      }
     }
   }
 

@@ -105,4 +105,79 @@ cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float*
   return cudaGetLastError();
 }
 
+// straight-line FMA body of N instructions (N * 16 bytes of SASS), for instruction-fetch interference experiments
+template <int N>
+__device__ __forceinline__ void big_body(float& a, float& b, float& c, float& d) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i) {
+    a = fmaf(a, 1.0f + 1e-6f * (float)(i + 1), 0.5f);
+    b = fmaf(b, 1.0f - 1e-6f * (float)(i + 1), 0.25f);
+    c = fmaf(c, 1.0f + 2e-6f * (float)(i + 1), 0.125f);
+    d = fmaf(d, 1.0f - 2e-6f * (float)(i + 1), 0.0625f);
+  }
+}
+
+__global__ void debug_spin_kernel(long long cycles, int mode, float* sink, long long sink_floats) {
+  extern __shared__ uint8_t spin_smem[];
+  const long long t0 = clock64();
+  float a = (float)threadIdx.x, b = 1.f, c = 2.f, d = 3.f;
+  int iter = 0;
+  while (clock64() - t0 < cycles) {
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        a = fmaf(a, 1.0001f, 0.5f); b = fmaf(b, 0.9999f, 0.25f); c = fmaf(c, 1.0002f, 0.125f); d = fmaf(d, 0.9998f, 0.0625f);
+      }
+    } else if (mode == 1) {
+      __nanosleep(1000);
+    } else if (mode == 6) {
+      big_body<1536>(a, b, c, d);   // 24 KB loop body: fits the 32 KB L1.5 instruction cache
+    } else if (mode == 9) {
+      big_body<1792>(a, b, c, d);   // 28 KB
+    } else if (mode == 10) {
+      big_body<1920>(a, b, c, d);   // 30 KB
+    } else if (mode == 11) {
+      big_body<2048>(a, b, c, d);   // 32 KB
+    } else if (mode == 12) {
+      big_body<2304>(a, b, c, d);   // 36 KB
+    } else if (mode == 8) {
+      big_body<2560>(a, b, c, d);   // 40 KB loop body: just above the L1.5 size
+    } else if (mode == 7) {
+      big_body<4096>(a, b, c, d);   // 64 KB loop body: streams from L2 on every trip
+    } else if (mode >= 4) {  // trajectory-like write pattern: 64 KB per CTA every ~8 us; mode 4 = st.global, mode 5 = bulk store
+      uint8_t* dst = reinterpret_cast<uint8_t*>(sink) + ((size_t)blockIdx.x * 64 + (size_t)(iter & 63) * gridDim.x * 64) * 1024;
+      if (mode == 4) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x) d4[i] = make_float4(a, b, c, d);
+      } else if (threadIdx.x == 0) {
+        bulk_store_1d(dst, spin_smem, 32768);
+        bulk_store_1d(dst + 32768, spin_smem + 32768, 32768);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+      ++iter;
+      const long long t1 = clock64();
+      while (clock64() - t1 < 15000) __nanosleep(200);
+    } else {  // mode 2: streaming float4 stores over the whole sink buffer (mode 3: loads), tiny code
+      float4* s4 = reinterpret_cast<float4*>(sink);
+      const long long n4 = sink_floats / 4, stride = (long long)gridDim.x * blockDim.x;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        if (mode == 2) s4[i] = make_float4(a, b, c, d);
+        else { const float4 v = s4[i]; a += v.x; b += v.y; c += v.z; d += v.w; }
+        if ((i & 0xfff) == 0 && clock64() - t0 >= cycles) break;
+      }
+    }
+  }
+  if (a + b + c + d == 123.456f) sink[0] = a + (float)spin_smem[0];
+}
+
+cudaError_t launch_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
+                              long long sink_floats, cudaStream_t stream) {
+  if (blocks <= 0 || threads <= 0 || threads > 1024 || smem_bytes < 0) { g_where = "bad spin config"; return cudaErrorInvalidValue; }
+  if (smem_bytes > 48 * 1024)
+    TB_TRY(cudaFuncSetAttribute(debug_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "smem attr");
+  debug_spin_kernel<<<blocks, threads, smem_bytes, stream>>>(cycles, mode, sink, sink_floats);
+  return cudaGetLastError();
+}
+
 }  // namespace tb
