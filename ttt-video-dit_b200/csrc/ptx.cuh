@@ -65,13 +65,26 @@ static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar_addr, uint32_
          (int)threadIdx.x, bar_addr, parity);
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// slow path out of line: the kernels are instruction-cache sensitive and have dozens of wait sites
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   // try_wait itself may sleep for a hardware-defined interval, so the clock is checked on every poll
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if ((clock64() - t0) > 4000000000LL) mbar_timeout_trap(smem_u32(bar), parity);
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((clock64() - t0) > 4000000000LL) mbar_timeout_trap(bar_addr, parity);
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05.mma operand reads)

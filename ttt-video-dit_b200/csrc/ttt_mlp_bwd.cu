@@ -724,8 +724,12 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     const int r = g % kRing;
     const int t0 = g * G;
     const int t1 = (t0 + G < NC) ? t0 + G : NC;
-    cudaError_t e = launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0, t1 - t0,
-                                          img[r], b1img[r], b2img[r], (int)slots, sd.sT);
+    // compact (L1.5-resident) trajectory kernel by default; TTT_B200_TRAJ=legacy runs the forward kernel in trajectory
+    // mode instead (same images up to fp32 summation order; 48 KB loop that disturbs the K-side kernel's instruction fetch)
+    static const bool legacy_traj = [] { const char* v = getenv("TTT_B200_TRAJ"); return v && v[0] == 'l'; }();
+    cudaError_t e = (legacy_traj ? launch_mlp_trajectory : launch_mlp_trajectory_compact)(
+        XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0, t1 - t0, img[r], b1img[r], b2img[r], (int)slots,
+        sd.sT);
     if (e != cudaSuccess) return e;
     if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;

@@ -43,6 +43,25 @@ struct BwdQParams {
   int H, NC, img_slots, G, t0;   // step s = t0 + blockIdx.x uses image slot blockIdx.x + 1
 };
 
+// rolled (code-size) versions of bwd_common.cuh's mma_hid (N = 64, B K-major, no accumulate) and mma_tok
+__device__ __forceinline__ void mma_hid_rolled(uint32_t d0, uint32_t d1, uint32_t a_tile, uint32_t b_tile) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+  const uint64_t db = make_desc_sw128(b_tile, 16, 1024);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const uint64_t da = make_desc_sw128(a_tile + h * 16384, 16, 1024);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) umma_ss(h ? d1 : d0, desc_advance(da, 32 * k), desc_advance(db, 32 * k), idesc, k > 0);
+  }
+}
+__device__ __forceinline__ void mma_tok_rolled(uint32_t d, uint32_t a_tile, uint32_t b_tile) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+  const uint64_t da = make_desc_sw128(a_tile, 0, 1024);
+  const uint64_t db = make_desc_sw128(b_tile, 1024, 1024);
+#pragma unroll 1
+  for (int k = 0; k < 16; ++k) umma_ss(d, desc_advance(da, 2048 * k), desc_advance(db, 2048 * k), idesc, k > 0);
+}
+
 __global__ void __launch_bounds__(256, 1)
 ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const BwdQParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -100,40 +119,36 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_load_2d(smem + QS_TDO, &tmDO, 0, (int)row, bar_qd);
   }
   uint32_t mma_phase = 0;
-  uint32_t g1p[32];
   mbar_wait(bar_w, 0);
   mbar_wait(bar_qd, 0);
 
   // ===== Q1 MMA: Zbar1^T = W1 . Q^T -> (S0,S1)
   if (tid == 0) {
     tc_fence_after();
-    mma_hid(tmem + QT_S0, tmem + QT_S1, sbase + QS_W1I, sbase + QS_TQ, false, 64, false);
+    mma_hid_rolled(tmem + QT_S0, tmem + QT_S1, sbase + QS_W1I, sbase + QS_TQ);
     tc_commit(mma_bar);
   }
   MMA_WAIT();
-  // ===== Q2 [H]: Xbar2 tile, gelu'(Zbar1)
+  // ===== Q2 [H]: Xbar2 tile, gelu'(Zbar1) (bf16, parked in the ZB tile until Q6 overwrites it in place).  Rolled
+  //       16-column chunks: this kernel must stay inside the 32 KB L1.5 instruction cache (see ttt_mlp_traj.cu)
   {
     const uint32_t src = tmem + lane_addr + (half ? QT_S1 : QT_S0);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {  // one 16-byte chunk (8 tokens) per trip
+      float v[8], g[8];
+      tmem_ld8(src + 8 * c, reinterpret_cast<uint32_t*>(v));
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float a0, a1;
-        v[i] = gelu1(v[i] + b1t, a0);
-        v[i + 1] = gelu1(v[i + 1] + b1t, a1);
-        g1p[16 * c + i / 2] = pack_bf16(a0, a1);
-      }
-      st_row32(sbase + QS_XB, j, 4 * c, v);
+      for (int i = 0; i < 8; ++i) v[i] = gelu1(v[i] + b1t, g[i]);
+      st_shared_v4(sbase + QS_XB + sw128_off(j, c), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      st_shared_v4(sbase + QS_ZB + sw128_off(j, c), pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
     }
   }
   PHASE_SYNC();
   // ===== Q3 MMA: Zbar2 = Xbar2 . W2 -> S2 (rows duplicated on lanes 64-127)
   if (tid == 0) {
     tc_fence_after();
-    mma_tok(tmem + QT_S2, sbase + QS_XB, sbase + QS_W2I, false);
+    mma_tok_rolled(tmem + QT_S2, sbase + QS_XB, sbase + QS_W2I);
     tc_commit(mma_bar);
   }
   MMA_WAIT();
@@ -185,27 +200,25 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // ===== Q5 MMA: dXbar2^T = W2 . dZbar2^T -> (S0,S1)
   if (tid == 0) {
     tc_fence_after();
-    mma_hid(tmem + QT_S0, tmem + QT_S1, sbase + QS_W2I, sbase + QS_TT0, false, 64, false);
+    mma_hid_rolled(tmem + QT_S0, tmem + QT_S1, sbase + QS_W2I, sbase + QS_TT0);
     tc_commit(mma_bar);
   }
   MMA_WAIT();
-  // ===== Q6 [H]: dZbar1 = dXbar2 * gelu'(Zbar1) -> ZB tile ; sum_i dZbar1 -> qb1
+  // ===== Q6 [H]: dZbar1 = dXbar2 * gelu'(Zbar1) -> ZB tile (in place) ; sum_i dZbar1 -> qb1
   {
     const uint32_t src = tmem + lane_addr + (half ? QT_S1 : QT_S0);
     float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[8];
+      uint32_t g0, g1, g2, g3;
+      tmem_ld8(src + 8 * c, reinterpret_cast<uint32_t*>(v));
+      ld_shared_v4(sbase + QS_ZB + sw128_off(j, c), g0, g1, g2, g3);
       tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const uint32_t gp1 = g1p[16 * c + i / 2];
-        v[i] *= bf16_lo(gp1);
-        v[i + 1] *= bf16_hi(gp1);
-        acc += v[i] + v[i + 1];
-      }
-      st_row32(sbase + QS_ZB, j, 4 * c, v);
+      v[0] *= bf16_lo(g0); v[1] *= bf16_hi(g0); v[2] *= bf16_lo(g1); v[3] *= bf16_hi(g1);
+      v[4] *= bf16_lo(g2); v[5] *= bf16_hi(g2); v[6] *= bf16_lo(g3); v[7] *= bf16_hi(g3);
+      acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      st_shared_v4(sbase + QS_ZB + sw128_off(j, c), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
     p.qb1[((size_t)bh * p.G + sl) * 256 + j] = acc;
   }
@@ -213,7 +226,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // ===== Q7 MMA: dQ_u = dZbar1 . W1 -> S2 ; factor tiles -> global scratch
   if (tid == 0) {
     tc_fence_after();
-    mma_tok(tmem + QT_S2, sbase + QS_ZB, sbase + QS_W1I, false);
+    mma_tok_rolled(tmem + QT_S2, sbase + QS_ZB, sbase + QS_W1I);
     tc_commit(mma_bar);
     uint8_t* dst = p.qt + ((size_t)bh * p.G + sl) * 73728;
     bulk_store_1d(dst, smem + QS_XB, 32768);
