@@ -48,9 +48,9 @@ import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import _lib, mlp_tk
-buf = torch.zeros(8192, dtype=torch.int32, device='cuda')
+buf = torch.zeros(16384, dtype=torch.int32, device='cuda')
 print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
-B,H,NC,G = 1,48,int(os.environ.get('TTT_TIMING_NC','64')),16
+B,H,NC,G = 1,int(os.environ.get('TTT_TIMING_H','48')),int(os.environ.get('TTT_TIMING_NC','64')),16
 d = O.make_inputs(B,H,NC,seed=1)
 bf = lambda t: t.to(torch.bfloat16).cuda()
 prm = [d[k].cuda().requires_grad_(True) for k in ('ln_w','ln_b','W1','b1','W2','b2')]
@@ -80,12 +80,14 @@ for rep in range(2):
         ngr = (NC + G - 1) // G
         base = None
         for gi in range(min(ngr, 27) - 1, -1, -1):
-            st = [x & 0xffffffff for x in t[512+gi*128:512+gi*128+48]]; en = [x & 0xffffffff for x in t[512+gi*128+64:512+gi*128+64+48]]
+            st = [x & 0xffffffff for x in t[512+gi*128:512+gi*128+min(H,48)]]; en = [x & 0xffffffff for x in t[512+gi*128+64:512+gi*128+64+min(H,48)]]
             if base is None: base = min(st)
             ss = sorted((x-base)/1e3 for x in st); ee = sorted((x-base)/1e3 for x in en)
             print('group %%2d: first start %%8.1f last start %%8.1f | first end %%8.1f last end %%8.1f  (us)' %% (gi, ss[0], ss[-1], ee[0], ee[-1]), flush=True)
-            sts = [x & 0xffffffff for x in t[4096+gi*32:4096+gi*32+16]]
-            print('          step durations us (t_hi..t_lo):', [round(((sts[k-1]-sts[k]) & 0xffffffff)/1e3,1) for k in range(15,0,-1) if sts[k] and sts[k-1]], flush=True)
+        sts = [x & 0xffffffff for x in t[4096:4096+NC]]
+        dur = [round(((sts[k-1]-sts[k]) & 0xffffffff)/1e3,1) for k in range(NC-1,0,-1)]
+        print('step durations us (t = NC-1 .. 1; launch boundaries show as long steps):', dur, flush=True)
+        print('sum of step durations us:', round(sum(dur),1), ' median', sorted(dur)[len(dur)//2], flush=True)
     buf.zero_()
 """ % (ROOT, ROOT, ROOT),
     "timeline": """

@@ -51,6 +51,14 @@ def test_backward_matches_autograd_of_eager(B, H, NC, G):
     assert not bad, f"rel errors above 1e-2: {bad} (all: {errs})"
 
 
+def test_backward_many_launch_units():
+    # 10 checkpoint groups of 4 -> launch units {9}, {6-8}, {3-5}, {0-2}: multi-group trajectory launches, ring-buffer reuse
+    d = O.make_inputs(1, 2, 40, seed=45)
+    errs = errors(d, 4)
+    bad = {k: v for k, v in errs.items() if not (v < 1e-2)}
+    assert not bad, f"rel errors above 1e-2: {bad} (all: {errs})"
+
+
 def test_backward_golden_reference_fixture():
     fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ttt_mlp_ref.pt"), weights_only=False)[1]
     c = fx["cfg"]

@@ -41,7 +41,7 @@ cudaError_t launch_mlp_trajectory(const void* XK, const void* XV, const void* la
                                   uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream);
 cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                           const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
-                                          const float* b2c, int B, int H, int NC, int K, int k, int t0, int nsteps,
+                                          const float* b2c, int B, int H, int NC, int K, int G, int t0, int t_end,
                                           uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream);
 size_t mlp_backward_workspace_bytes(int B, int H, int G);
 cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,

@@ -230,10 +230,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();  // b2t / etas visible
       TICK(0);
 #ifdef TTT_PHASE_TIMING
-    if (p.dbg && tid == 0 && blockIdx.x == 0 && p.t_lo / p.G < 27) {  // wall-clock stamp of every step (block 0)
+    if (p.dbg && tid == 0 && blockIdx.x == 0 && t < 4000) {  // wall-clock stamp of every step (block 0)
       unsigned long long gs;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gs));
-      p.dbg[4096 + (p.t_lo / p.G) * 32 + (t - p.t_lo)] = (unsigned)gs;
+      p.dbg[4096 + t] = (unsigned)gs;
     }
 #endif
 
@@ -648,13 +648,16 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }  // namespace bwd
 
 // ------------------------------------------------------------------------------------------------ host
-// Recompute state is kept in a ring of kRing group buffers so that the trajectory / Q-side kernels of later groups run
-// ahead of the sequential K-side kernel (three streams).
+// Recompute state is kept in a ring of kRing buffers so that the trajectory / Q-side kernels of later steps run ahead
+// of the sequential K-side kernel (three streams).  One K-side launch ("unit") may cover up to kSuper checkpoint groups
+// (the trajectory kernel then replays the groups of a unit concurrently, one CTA per (sequence, group)).  Measured on
+// B200 (profiles/r01_launch_units.log): units of 2-3 groups save the ~50 us per-launch cost but lose more to a longer
+// pipeline fill and to trajectory CTAs that take the SMs the next K-side launch is waiting for, so kSuper = 1.
 constexpr int kRing = 3;
+constexpr int kSuper = 1;
 
 size_t mlp_backward_workspace_bytes(int B, int H, int G) {
-  const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
-  const size_t g = (size_t)G;
+  const size_t bh = (size_t)B * H, g = (size_t)G * kSuper, slots = g + 1;
   return bh * (kRing * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + kRing * (g * 73728 + g * 1024 + g * 256) +
                2 * 65536 + 1024 + 256 + 32768) + 1024;
 }
@@ -666,7 +669,8 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
                                 size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) { g_where = "bad sizes"; return cudaErrorInvalidValue; }
   if (workspace_bytes < mlp_backward_workspace_bytes(B, H, G)) { g_where = "workspace"; return cudaErrorInvalidValue; }
-  const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
+  const int Gs = G * kSuper;  // steps per ring buffer = stride of the per-step scratch arrays
+  const size_t bh = (size_t)B * H, slots = (size_t)Gs + 1;
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   w = reinterpret_cast<uint8_t*>(((uintptr_t)w + 1023) & ~(uintptr_t)1023);
   uint8_t* img[kRing]; float *b1img[kRing], *b2img[kRing];
@@ -679,9 +683,9 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   float* db1s = reinterpret_cast<float*>(w); w += bh * 1024;
   float* db2s = reinterpret_cast<float*>(w); w += bh * 256;
   uint8_t* qt[kRing]; float *qb1[kRing], *qb2[kRing];   // Q-side factor tiles / vectors of a group
-  for (int i = 0; i < kRing; ++i) { qt[i] = w; w += bh * (size_t)G * 73728; }
-  for (int i = 0; i < kRing; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 1024; }
-  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 256; }
+  for (int i = 0; i < kRing; ++i) { qt[i] = w; w += bh * (size_t)Gs * 73728; }
+  for (int i = 0; i < kRing; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 1024; }
+  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 256; }
 
   CUtensorMap tq, tk, tv, tdo;
   const uint64_t rows = (uint64_t)bh * NC * 64;
@@ -718,35 +722,47 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     }
   }
   const int K = (NC + G - 1) / G;
-  // group g -> ring buffer r = g % kRing: trajectory (images of W_{t0} .. W_{t1}) on stream T, then the Q-side kernel
+  // compact (L1.5-resident) trajectory kernel by default; TTT_B200_TRAJ=legacy runs the forward kernel in trajectory mode
+  // instead (one group per launch; 48 KB loop that disturbs the K-side kernel's instruction fetch)
+  static const bool legacy_traj = [] { const char* v = getenv("TTT_B200_TRAJ"); return v && v[0] == 'l'; }();
+  static const int super_env = [] { const char* v = getenv("TTT_B200_SUPER"); return v ? atoi(v) : kSuper; }();
+  const int m = legacy_traj ? 1 : (super_env < 1 ? 1 : (super_env > kSuper ? kSuper : super_env));
+  // units in processing order (descending steps): {first group, last group}; the first unit is the last group alone
+  int ulo[1 + 4096], uhi[1 + 4096], U = 0;
+  for (int g = K - 1; g >= 0;) {
+    const int lo = (U == 0) ? g : (g - m + 1 > 0 ? g - m + 1 : 0);
+    if (U > 4096) { g_where = "too many launch units"; return cudaErrorInvalidValue; }
+    ulo[U] = lo; uhi[U] = g; ++U;
+    g = lo - 1;
+  }
+  // unit u -> ring buffer r = u % kRing: trajectory (images of W_{t0} .. W_{t1}) on stream T, then the Q-side kernel
   // (steps t0 .. t1-1) on stream Q
-  auto recompute = [&](int g) -> cudaError_t {
-    const int r = g % kRing;
-    const int t0 = g * G;
-    const int t1 = (t0 + G < NC) ? t0 + G : NC;
-    // compact (L1.5-resident) trajectory kernel by default; TTT_B200_TRAJ=legacy runs the forward kernel in trajectory
-    // mode instead (same images up to fp32 summation order; 48 KB loop that disturbs the K-side kernel's instruction fetch)
-    static const bool legacy_traj = [] { const char* v = getenv("TTT_B200_TRAJ"); return v && v[0] == 'l'; }();
-    cudaError_t e = (legacy_traj ? launch_mlp_trajectory : launch_mlp_trajectory_compact)(
-        XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, g, t0, t1 - t0, img[r], b1img[r], b2img[r], (int)slots,
-        sd.sT);
+  auto recompute = [&](int u) -> cudaError_t {
+    const int r = u % kRing;
+    const int t0 = ulo[u] * G;
+    const int t1 = ((uhi[u] + 1) * G < NC) ? (uhi[u] + 1) * G : NC;
+    cudaError_t e = legacy_traj
+                        ? launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, ulo[u], t0, t1 - t0,
+                                                img[r], b1img[r], b2img[r], (int)slots, sd.sT)
+                        : launch_mlp_trajectory_compact(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, G, t0, t1,
+                                                        img[r], b1img[r], b2img[r], (int)slots, sd.sT);
     if (e != cudaSuccess) return e;
     if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;
     e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[r], b1img[r], b2img[r], qt[r], qb1[r], qb2[r], dXQ, dlnw, dlnb,
-                              (int)bh, H, NC, (int)slots, G, t0, t1 - t0, sd.sQ);
+                              (int)bh, H, NC, (int)slots, Gs, t0, t1 - t0, sd.sQ);
     if (e != cudaSuccess) return e;
     return cudaEventRecord(sd.evQ[r], sd.sQ);
   };
   TB_TRY(cudaEventRecord(sd.fork, stream), "fork record");
   TB_TRY(cudaStreamWaitEvent(sd.sT, sd.fork, 0), "fork wait");
   TB_TRY(cudaStreamWaitEvent(sd.sQ, sd.fork, 0), "fork wait");
-  for (int i = 0; i < kRing && K - 1 - i >= 0; ++i) TB_TRY(recompute(K - 1 - i), "trajectory / Q launch");
-  for (int g = K - 1; g >= 0; --g) {
-    const int r = g % kRing;
-    const int t0 = g * G;
-    const int t1 = (t0 + G < NC) ? t0 + G : NC;
-    const bool last = (g == K - 1);
+  for (int i = 0; i < kRing && i < U; ++i) TB_TRY(recompute(i), "trajectory / Q launch");
+
+  for (int u = 0; u < U; ++u) {
+    const int r = u % kRing;
+    const int t0 = ulo[u] * G;
+    const int t1 = ((uhi[u] + 1) * G < NC) ? (uhi[u] + 1) * G : NC;
     TB_TRY(cudaStreamWaitEvent(stream, sd.evQ[r], 0), "wait Q-side");
     bwd::BwdParams p{};
     p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
@@ -754,7 +770,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.img = img[r]; p.b1img = b1img[r]; p.b2img = b2img[r];
     p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
     p.x2spill = x2s;
-    p.qt = qt[r]; p.qb1 = qb1[r]; p.qb2 = qb2[r]; p.G = G;
+    p.qt = qt[r]; p.qb1 = qb1[r]; p.qb2 = qb2[r]; p.G = Gs;
     p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
     p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = reinterpret_cast<__nv_bfloat16*>(dEta);
     p.dlnw = dlnw; p.dlnb = dlnb;
@@ -762,15 +778,15 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.H = H; p.NC = NC; p.img_slots = (int)slots;
     p.t_hi = t1 - 1;
     p.t_lo = t0; p.t0 = t0;
-    p.first = last ? 1 : 0;
+    p.first = (u == 0) ? 1 : 0;
     { const char* dg = getenv("TTT_DBG_GROUP"); p.dbg_group = dg ? atoi(dg) : 0; }
-    p.dbg = g_timing_buf;  // observers: the last launch (g == 0, a full group) wins; per-group stamps are kept
+    p.dbg = g_timing_buf;  // observers: the launch whose t_lo / G equals TTT_DBG_GROUP; per-launch stamps are kept
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
-    if (g >= kRing) {  // ring buffer r is free again once this launch is done: recompute group g - kRing into it
+    if (u + kRing < U) {  // ring buffer r is free again once this launch is done: recompute unit u + kRing into it
       TB_TRY(cudaEventRecord(sd.evR[r], stream), "record reverse");
       TB_TRY(cudaStreamWaitEvent(sd.sT, sd.evR[r], 0), "wait reverse");
-      TB_TRY(recompute(g - kRing), "trajectory / Q launch");
+      TB_TRY(recompute(u + kRing), "trajectory / Q launch");
     }
   }
   return cudaSuccess;

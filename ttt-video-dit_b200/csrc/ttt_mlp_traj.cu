@@ -45,8 +45,10 @@ constexpr uint32_t TM_W1 = 0, TM_W2 = 128, TM_D1 = 256, TM_D3 = 256, TM_D2 = 384
 struct TrajParams {
   const __nv_bfloat16* last_eta;        // [B,H,NC,64]
   const float *ln_w, *ln_b;             // [H,64]
-  const float *W1, *b1, *W2, *b2;       // checkpoint arrays [BH][K]...; this launch starts from checkpoint k
-  int NC, H, K, k, t0, nsteps, img_slots;
+  const float *W1, *b1, *W2, *b2;       // checkpoint arrays [BH][K]...
+  // one launch covers the steps [t0, t_end) of nsub = gridDim.y consecutive checkpoint groups of G steps: CTA (bh, sub)
+  // replays group sub from its own checkpoint (index t0 / G + sub) into the image slots sub * G ...
+  int NC, H, K, G, t0, t_end, img_slots;
   uint8_t* img;                         // [BH][img_slots] x 64 KB
   float *b1img, *b2img;                 // [BH][img_slots][256], [BH][img_slots][64]
 };
@@ -57,7 +59,11 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x, head = bh % p.H;
-  const int n = p.nsteps;
+  const int sub = blockIdx.y;
+  const int my_t0 = p.t0 + sub * p.G;
+  const int n = (my_t0 + p.G < p.t_end) ? p.G : p.t_end - my_t0;
+  // the state after the last step of a group is the next group's checkpoint: only the last group of the launch stores it
+  const bool store_last = (sub == (int)gridDim.y - 1);
   const int half = warp >> 2, j = tid;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
 
@@ -81,7 +87,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     tma_prefetch_desc(&tmV);
   }
   if (warp == 0) tmem_alloc<512>(tmem_ptr);
-  const size_t st = (size_t)bh * p.K + p.k;
+  const size_t st = (size_t)bh * p.K + (size_t)(my_t0 / p.G);
   if (tid < 64) {
     lnw[tid] = p.ln_w[head * 64 + tid];
     lnb[tid] = p.ln_b[head * 64 + tid];
@@ -92,10 +98,11 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const size_t row_base = ((size_t)bh * p.NC + p.t0) * CS;
-  uint8_t* img = p.img + (size_t)bh * p.img_slots * 65536;
-  float* b1img = p.b1img + (size_t)bh * p.img_slots * HID;
-  float* b2img = p.b2img + (size_t)bh * p.img_slots * F;
+  const size_t row_base = ((size_t)bh * p.NC + my_t0) * CS;
+  const size_t slot0 = (size_t)bh * p.img_slots + (size_t)sub * p.G;
+  uint8_t* img = p.img + slot0 * 65536;
+  float* b1img = p.b1img + slot0 * HID;
+  float* b2img = p.b2img + slot0 * F;
 
   if (tid == 0) {
     mbar_expect_tx(&tma_bar[0], 16384);
@@ -343,8 +350,9 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    const bool store_img = store_last || it + 1 < n;
     if (tid == 0) {
-      bulk_store_1d(img + (size_t)(it + 1) * 65536, smem + SM_W1B, 32768);
+      if (store_img) bulk_store_1d(img + (size_t)(it + 1) * 65536, smem + SM_W1B, 32768);
       if (it + 1 < n) issue_p1(it + 1);  // runs under the W2 conversion below
     }
 #pragma unroll 1
@@ -354,13 +362,15 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc_wait_ld();
       st_row16(sbase + SM_W2B, j, 2 * c, v);
     }
-    b1img[(size_t)(it + 1) * HID + j] = b1r;
-    if (tid < 64) b2img[(size_t)(it + 1) * F + tid] = b2s[tid];  // b2s was updated by the same thread in P6
+    if (store_img) {
+      b1img[(size_t)(it + 1) * HID + j] = b1r;
+      if (tid < 64) b2img[(size_t)(it + 1) * F + tid] = b2s[tid];  // b2s was updated by the same thread in P6
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
-      bulk_store_1d(img + (size_t)(it + 1) * 65536 + 32768, smem + SM_W2B, 32768);
+      if (store_img) bulk_store_1d(img + (size_t)(it + 1) * 65536 + 32768, smem + SM_W2B, 32768);
       bulk_commit();
     }
   }
@@ -375,16 +385,19 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
 cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                           const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
-                                          const float* b2c, int B, int H, int NC, int K, int k, int t0, int nsteps,
+                                          const float* b2c, int B, int H, int NC, int K, int G, int t0, int t_end,
                                           uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream) {
-  if (nsteps <= 0 || nsteps + 1 > img_slots) { g_where = "bad trajectory window"; return cudaErrorInvalidValue; }
+  if (G <= 0 || t0 % G != 0 || t_end <= t0 || t_end > NC || t_end - t0 + 1 > img_slots) {
+    g_where = "bad trajectory window";
+    return cudaErrorInvalidValue;
+  }
   const uint64_t rows = (uint64_t)B * H * NC * traj::CS;
   CUtensorMap tk, tv;
   if (make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows)) return cudaErrorInvalidValue;
   traj::TrajParams p{};
   p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
   p.ln_w = ln_w; p.ln_b = ln_b; p.W1 = W1c; p.b1 = b1c; p.W2 = W2c; p.b2 = b2c;
-  p.NC = NC; p.H = H; p.K = K; p.k = k; p.t0 = t0; p.nsteps = nsteps; p.img_slots = img_slots;
+  p.NC = NC; p.H = H; p.K = K; p.G = G; p.t0 = t0; p.t_end = t_end; p.img_slots = img_slots;
   p.img = img; p.b1img = b1img; p.b2img = b2img;
   static bool attr_done = false;
   if (!attr_done) {
@@ -392,7 +405,8 @@ cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const 
     attr_done = true;
   }
   g_where = "trajectory launch";
-  traj::ttt_mlp_traj_kernel<<<B * H, traj::NT, traj::SM_TOTAL, stream>>>(tk, tv, p);
+  const dim3 grid(B * H, (t_end - t0 + G - 1) / G);
+  traj::ttt_mlp_traj_kernel<<<grid, traj::NT, traj::SM_TOTAL, stream>>>(tk, tv, p);
   return cudaGetLastError();
 }
 

@@ -62,9 +62,14 @@ LAUNCHES_FWD = 1  # one persistent scan kernel per forward call
 _last_groups = [1]
 
 
+SUPER = 1  # checkpoint groups per backward launch unit (kSuper in csrc/ttt_mlp_bwd.cu)
+
+
 def launches_bwd():
-    """2 memsets are library calls; our kernels per checkpoint group: trajectory + Q-side kernel + sequential K-side kernel."""
-    return 3 * _last_groups[0]
+    """2 memsets are library calls; our kernels per launch unit: trajectory + Q-side kernel + sequential K-side kernel."""
+    groups = _last_groups[0]
+    units = 1 + (groups - 1 + SUPER - 1) // SUPER
+    return 3 * units
 
 
 _ws_cache = {}
