@@ -86,6 +86,16 @@ int ttt_b200_linear_backward(const void* XQ, const void* XK, const void* XV, con
 int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void* out, int B, int T, int H,
                                float scale, void* stream);
 
+/* Training pair of the same attention.  _forward_lse additionally writes lse2 f32 [B,H,T] = log2-domain log-sum-exp of
+ * every query row (what the library's flash-attention forward saves for its backward).  _backward computes the gradient
+ * that autograd takes through F.scaled_dot_product_attention at dit.py:196-198: dq/dk/dv bf16 [B,T,H,64] from
+ * q, k, v, out, dout (same layout) and lse2; delta_scratch: f32 [B,H,T] device scratch (rowsum(dout * out)). */
+int ttt_b200_attention_forward_lse(const void* q, const void* k, const void* v, void* out, float* lse2, int B, int T, int H,
+                                   float scale, void* stream);
+int ttt_b200_attention_backward(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                                const float* lse2, float* delta_scratch, void* dq, void* dk, void* dv, int B, int T, int H,
+                                float scale, void* stream);
+
 /* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
  * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in
  * ttt/models/cogvideo/dit.py:90-103,213-222,241-266.  Tensors are bf16 [B, L, E], text tokens first

@@ -227,6 +227,40 @@ for label, mode, blocks, threads, smem in [('code28K 100x256', 9, 100, 256, 200*
         sts = [x & 0xffffffff for x in t[4096+gi*32:4096+gi*32+16]]
         print('%%-14s group %%d step us:' %% (label, gi), [round(((sts[kk-1]-sts[kk]) & 0xffffffff)/1e3,1) for kk in range(15,0,-1)], flush=True)
 """ % (ROOT, ROOT, ROOT),
+    "attn_bwd": """
+import torch, sys, time
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ttt_oracle as O
+from ttt_video_dit_b200 import attention
+for (B,T,H) in [(1,128,1),(1,256,1),(2,300,3),(1,1000,2),(1,129,1)]:
+    g = torch.Generator().manual_seed(1000 + T)
+    q, k, v, go = (torch.randn(B, T, H, 64, generator=g).to(torch.bfloat16) for _ in range(4))
+    q = q * 2.0
+    qc, kc, vc = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    try:
+        out = attention.sdpa_bthd(qc, kc, vc); out.backward(go.cuda()); torch.cuda.synchronize()
+    except Exception as ex:
+        print((B,T,H), 'EXC', repr(ex)[:300], flush=True); break
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    tr = lambda t: t.permute(0, 2, 1, 3)
+    ref = O.sdpa_math(tr(qr), tr(kr), tr(vr)).permute(0, 2, 1, 3); ref.backward(go.float())
+    print((B,T,H), 'out', '%%.2e' %% O.rel_err(out.float().cpu(), ref.detach()), {n: float('%%.2e' %% O.rel_err(a.grad.float().cpu(), b.grad)) for n,a,b in (('dq',qc,qr),('dk',kc,kr),('dv',vc,vr))}, flush=True)
+B,T,H = 1,18048,48
+q, k, v, go = (torch.randn(B, T, H, 64, device='cuda').to(torch.bfloat16) for _ in range(4))
+qc, kc, vc = (t.requires_grad_(True) for t in (q, k, v))
+import torch.nn.functional as F
+for rep in range(2):
+    torch.cuda.synchronize(); t0=time.time()
+    out = attention.sdpa_bthd(qc, kc, vc); torch.cuda.synchronize(); t1=time.time()
+    out.backward(go); torch.cuda.synchronize(); t2=time.time()
+    print('ours  T=18048 H=48: fwd %%.2f ms bwd %%.2f ms (bwd %%.0f TF/s algorithmic)' %% ((t1-t0)*1e3, (t2-t1)*1e3, 2.5*4*T*T*64*H/(t2-t1)/1e12), flush=True)
+qh, kh, vh = (t.detach().permute(0,2,1,3).requires_grad_(True) for t in (q,k,v))
+for rep in range(2):
+    torch.cuda.synchronize(); t0=time.time()
+    o2 = F.scaled_dot_product_attention(qh, kh, vh); torch.cuda.synchronize(); t1=time.time()
+    o2.backward(go.permute(0,2,1,3)); torch.cuda.synchronize(); t2=time.time()
+    print('torch SDPA: fwd %%.2f ms bwd %%.2f ms' %% ((t1-t0)*1e3, (t2-t1)*1e3), flush=True)
+""" % (ROOT, ROOT),
     "bwd_direct": """
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')

@@ -5,8 +5,8 @@ for tensors kept in the Linear-output layout [B, T, H, 64]; ``local_attention`` 
 ``SeqModelingBlock._attn_forward`` (dit.py:163-211): per segment i, tokens = text chunk i + latent frames
 [12 i, 12 i + 13); q/k/v Linear -> per-head LayerNorm(q), (k) -> RoPE on the video part (segment-local positions) ->
 attention -> o Linear; text rows written, video rows accumulated and divided by the overlap count.
-Round-1 state: forward only (sampling path); the Linears / LayerNorm / RoPE around the kernel are the same library /
-elementwise ops the reference uses.
+``sdpa_bthd`` is differentiable (csrc/attn_bwd.cu); the Linears / LayerNorm / RoPE around the kernel are the same
+library / elementwise ops the reference uses.
 """
 import math
 
@@ -16,17 +16,54 @@ import torch.nn.functional as F
 from . import _lib
 
 
-def sdpa_bthd(q, k, v, scale=None):
-    """q, k, v: bf16 [B, T, H, 64] contiguous -> out [B, T, H, 64] (non-causal softmax(q k^T * scale) v)."""
+def _check_qkv(q, k, v):
     B, T, H, D = q.shape
     if D != 64:
         raise RuntimeError("attention kernel is specialised for head_dim 64")
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == q.shape):
             raise RuntimeError(f"{n} must be a contiguous CUDA bf16 tensor [B, T, H, 64]")
+    return B, T, H, D
+
+
+class _SDPA(torch.autograd.Function):
+    """Forward saves the per-row log-sum-exp; backward = ttt_b200_attention_backward (csrc/attn_bwd.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale):
+        B, T, H, D = _check_qkv(q, k, v)
+        out = torch.empty_like(q)
+        lse = torch.empty(B, H, T, device=q.device, dtype=torch.float32)
+        code = _lib.lib().ttt_b200_attention_forward_lse(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(lse),
+                                                         B, T, H, scale, _lib.current_stream())
+        _lib.check(code, "ttt_b200_attention_forward_lse")
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        B, T, H, D = q.shape
+        dout = dout.to(torch.bfloat16).contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        delta = torch.empty_like(lse)
+        p = _lib.ptr
+        code = _lib.lib().ttt_b200_attention_backward(p(q), p(k), p(v), p(out), p(dout), p(lse), p(delta), p(dq), p(dk), p(dv),
+                                                      B, T, H, ctx.scale, _lib.current_stream())
+        _lib.check(code, "ttt_b200_attention_backward")
+        return dq, dk, dv, None
+
+
+def sdpa_bthd(q, k, v, scale=None):
+    """q, k, v: bf16 [B, T, H, 64] contiguous -> out [B, T, H, 64] (non-causal softmax(q k^T * scale) v); differentiable."""
+    B, T, H, D = _check_qkv(q, k, v)
+    sc = float(scale if scale is not None else 1.0 / math.sqrt(D))
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return _SDPA.apply(q, k, v, sc)
     out = torch.empty_like(q)
-    code = _lib.lib().ttt_b200_attention_forward(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), B, T, H,
-                                                 float(scale if scale is not None else 1.0 / math.sqrt(D)), _lib.current_stream())
+    code = _lib.lib().ttt_b200_attention_forward(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), B, T, H, sc,
+                                                 _lib.current_stream())
     _lib.check(code, "ttt_b200_attention_forward")
     return out
 

@@ -47,7 +47,8 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(NT, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ Out, int T, int H, float scale_log2) {
+                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ Out, float* __restrict__ lse2,
+                int T, int H, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -184,6 +185,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // ---- epilogue: O / l -> bf16 -> out[b, q0 + tid, h, :]
   {
     const float inv = 1.f / l_run;
+    // row statistic for the backward (attn_bwd.cu): log2-domain log-sum-exp, P = exp2(S * scale_log2 - lse2)
+    if (lse2) lse2[((size_t)b * H + h) * T + q0 + tid] = m_run + log2f(l_run);
     __nv_bfloat16* og = Out + (((size_t)b * T + q0 + tid) * H + h) * D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -205,7 +208,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace attn
 
 // 4-D bf16 tensor [B][T][H][64] (innermost first: {64, H, T, B}), box {64, 1, 128, 1}, 128-B swizzle
-static int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H) {
+int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H) {
   static thread_local char detail[160];
   void* ptr = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -227,8 +230,8 @@ static int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H
   return 0;
 }
 
-cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, int B, int T, int H,
-                                     float scale, cudaStream_t stream) {
+cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, float* lse2, int B, int T,
+                                     int H, float scale, cudaStream_t stream) {
   if (B <= 0 || T < attn::BM || H <= 0) { g_where = "bad sizes (T must be >= 128)"; return cudaErrorInvalidValue; }
   CUtensorMap tq, tk, tv;
   if (make_bthd_tmap(&tq, Q, B, T, H) || make_bthd_tmap(&tk, K, B, T, H) || make_bthd_tmap(&tv, V, B, T, H))
@@ -240,7 +243,7 @@ cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V
   }
   g_where = "attention launch";
   dim3 grid((T + attn::BM - 1) / attn::BM, H, B);
-  attn::attn_fwd_kernel<<<grid, attn::NT, attn::SM_TOTAL, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(Out), T, H,
+  attn::attn_fwd_kernel<<<grid, attn::NT, attn::SM_TOTAL, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(Out), lse2, T, H,
                                                                      scale * 1.4426950408889634f);
   return cudaGetLastError();
 }

@@ -140,8 +140,27 @@ int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void
                                void* stream) {
   if (!q || !k || !v || !out) return fail(-1, "ttt_b200_attention_forward: null pointer argument");
   if (int rc = bind_device(q)) return rc;
-  return cuda_ret(tb::launch_attention_forward(q, k, v, out, B, T, H, scale, (cudaStream_t)stream),
+  return cuda_ret(tb::launch_attention_forward(q, k, v, out, nullptr, B, T, H, scale, (cudaStream_t)stream),
                   "ttt_b200_attention_forward");
+}
+
+int ttt_b200_attention_forward_lse(const void* q, const void* k, const void* v, void* out, float* lse2, int B, int T, int H,
+                                   float scale, void* stream) {
+  if (!q || !k || !v || !out || !lse2) return fail(-1, "ttt_b200_attention_forward_lse: null pointer argument");
+  if (int rc = bind_device(q)) return rc;
+  return cuda_ret(tb::launch_attention_forward(q, k, v, out, lse2, B, T, H, scale, (cudaStream_t)stream),
+                  "ttt_b200_attention_forward_lse");
+}
+
+int ttt_b200_attention_backward(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                                const float* lse2, float* delta_scratch, void* dq, void* dk, void* dv, int B, int T, int H,
+                                float scale, void* stream) {
+  if (!q || !k || !v || !out || !dout || !lse2 || !delta_scratch || !dq || !dk || !dv)
+    return fail(-1, "ttt_b200_attention_backward: null pointer argument");
+  if (int rc = bind_device(q)) return rc;
+  return cuda_ret(tb::launch_attention_backward(q, k, v, out, dout, lse2, delta_scratch, dq, dk, dv, B, T, H, scale,
+                                                (cudaStream_t)stream),
+                  "ttt_b200_attention_backward");
 }
 
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,

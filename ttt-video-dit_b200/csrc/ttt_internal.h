@@ -78,8 +78,11 @@ cudaError_t launch_linear_backward(const void* XQ, const void* XK, const void* X
 }  // namespace tb
 
 namespace tb {
-cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, int B, int T, int H,
-                                     float scale, cudaStream_t stream);
+cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V, void* Out, float* lse2, int B, int T,
+                                     int H, float scale, cudaStream_t stream);
+cudaError_t launch_attention_backward(const void* Q, const void* K, const void* V, const void* Out, const void* dOut,
+                                      const float* lse2, float* delta, void* dQ, void* dK, void* dV, int B, int T, int H,
+                                      float scale, cudaStream_t stream);
 }  // namespace tb
 
 namespace tb {
