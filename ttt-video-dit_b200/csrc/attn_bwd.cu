@@ -9,8 +9,9 @@
 // Two passes of ONE kernel template, no atomics and no fp32 dQ buffer (7 GEMMs instead of 5, deterministic):
 //   mode 0: CTA = one 128-key tile (stationary K_j, V_j), streams the query tiles, accumulates dK_j, dV_j in TMEM
 //   mode 1: CTA = one 128-query tile (stationary Q_i, dO_i), streams the key tiles, accumulates dQ_i in TMEM
-// In both modes S / dP are [128 query rows x 128 key columns] fp32 in TMEM; 256 threads = (row, 64-column half): no row
-// reductions are needed in the backward (lse2, delta are inputs), so the two warpgroups split the columns.  P and dS go
+// In both modes S / dP are [128 query rows x 128 key columns] fp32 in TMEM; 512 threads = (row, 32-column quarter): no row
+// reductions are needed in the backward (lse2, delta are inputs), so the four warpgroups simply split the columns
+// (16 warps per SM hide the tcgen05.ld / MUFU latencies of the element-wise pass).  P and dS go
 // to shared memory as bf16 [query][key] tiles (two 64-column SW128 blocks): read MN-major they are the A operand of the
 // dV / dK GEMMs (M = keys, K = queries), read K-major dS is the A operand of the dQ GEMM -- no transposes anywhere.
 // The accumulate GEMMs of iteration i and the S / dP GEMMs of iteration i+1 are issued as one batch.
@@ -28,7 +29,7 @@
 namespace tb {
 namespace attnb {
 
-constexpr int D = 64, BT = 128, NT = 256;
+constexpr int D = 64, BT = 128, NT = 512;
 constexpr uint32_t SM_FIX0 = 0;                   // stationary tile 0: K_j (mode 0) / Q_i (mode 1)       16 KB
 constexpr uint32_t SM_FIX1 = 16384;               // stationary tile 1: V_j (mode 0) / dO_i (mode 1)      16 KB
 constexpr uint32_t SM_STR0 = 32768;               // 2 x streamed tile 0: Q_i (mode 0) / K_j (mode 1)     32 KB
@@ -87,7 +88,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int own = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row = 32 * (warp & 3) + lane;  // query row of the S tile == TMEM lane
-  const int ch = warp >> 2;                // 64-column half of the S tile
+  const int ch = warp >> 2;                // 32-column quarter of the S tile
   const int ntiles = (T + BT - 1) / BT;
   const int own0 = min(own * BT, T - BT);  // first token of the stationary tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC);
@@ -161,24 +162,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     if (tid == 0 && i + 1 < ntiles) load_stream(i + 1);  // slot (i+1)&1 was last read by iteration i-1's GEMMs
 
-    // ---- P and dS for (row, column half ch)
+    // ---- P and dS for (row, column half ch); only a shifted-back tail tile needs the element masks
     const bool row_ok = (kMode == 1) || (row >= first_new);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    const float nlse = -lse_r, ndel = -del_r;
+    {
       float sv[32], dp[32];
-      tmem_ld32(tmem + lane_addr + TM_S + 64 * ch + 32 * c, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld32(tmem + lane_addr + TM_DP + 64 * ch + 32 * c, reinterpret_cast<uint32_t*>(dp));
+      tmem_ld32(tmem + lane_addr + TM_S + 32 * ch, reinterpret_cast<uint32_t*>(sv));
+      tmem_ld32(tmem + lane_addr + TM_DP + 32 * ch, reinterpret_cast<uint32_t*>(dp));
       tc_wait_ld();
+      if (first_new == 0) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const bool ok = row_ok && ((kMode == 0) || (64 * ch + 32 * c + e >= first_new));
-        const float pv = ok ? ex2(fmaf(sv[e], scale_log2, -lse_r)) : 0.f;
-        sv[e] = pv;
-        dp[e] = pv * (dp[e] - del_r) * scale;
+        for (int e = 0; e < 32; ++e) {
+          sv[e] = ex2(fmaf(sv[e], scale_log2, nlse));
+          dp[e] = sv[e] * ((dp[e] + ndel) * scale);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const bool ok = row_ok && ((kMode == 0) || (32 * ch + e >= first_new));
+          const float pv = ok ? ex2(fmaf(sv[e], scale_log2, nlse)) : 0.f;
+          sv[e] = pv;
+          dp[e] = pv * ((dp[e] + ndel) * scale);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t off = (uint32_t)ch * 16384 + sw128_off(row, 4 * c + q);
+        const uint32_t off = (uint32_t)(ch >> 1) * 16384 + sw128_off(row, 4 * (ch & 1) + q);
         if (kMode == 0)
           st_shared_v4(sbase + SM_P + off, pack_bf16(sv[8 * q], sv[8 * q + 1]), pack_bf16(sv[8 * q + 2], sv[8 * q + 3]),
                        pack_bf16(sv[8 * q + 4], sv[8 * q + 5]), pack_bf16(sv[8 * q + 6], sv[8 * q + 7]));
@@ -225,14 +234,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   // ---- epilogue: accumulators -> bf16 -> [b, own0 + row, h, :]
   {
-    // mode 0: warps 0-3 store dK (acc0), warps 4-7 store dV (acc1), 64 columns each; mode 1: both halves store 32 columns of dQ
-    __nv_bfloat16* dst = ((kMode == 0 && ch == 1) ? out1 : out0) + (((size_t)b * T + own0 + row) * H + h) * D;
-    const uint32_t src = tmem + lane_addr + ((kMode == 0 && ch == 1) ? TM_ACC1 : TM_ACC0);
-#pragma unroll
-    for (int c = 0; c < (kMode == 0 ? 2 : 1); ++c) {
-      const int col = (kMode == 0) ? 32 * c : 32 * ch;
+    // mode 0: warpgroups 0,1 store the two 32-column halves of dK (acc0), warpgroups 2,3 those of dV (acc1);
+    // mode 1: warpgroups 0,1 store dQ (acc0)
+    const bool second = (kMode == 0) && (ch >= 2);
+    if (kMode == 0 || ch < 2) {
+      __nv_bfloat16* dst = (second ? out1 : out0) + (((size_t)b * T + own0 + row) * H + h) * D;
+      const int col = 32 * (ch & 1);
       float o[32];
-      tmem_ld32(src + col, reinterpret_cast<uint32_t*>(o));
+      tmem_ld32(tmem + lane_addr + (second ? TM_ACC1 : TM_ACC0) + col, reinterpret_cast<uint32_t*>(o));
       tc_wait_ld();
 #pragma unroll
       for (int q = 0; q < 4; ++q)

@@ -7,10 +7,11 @@
 //
 // One CTA = 128 query rows of one (b,h); FlashAttention-style online softmax over 128-key tiles:
 //   S[128x128] = Q.K^T            tcgen05, A = Q tile (K-major), B = K tile (K-major), fp32 in TMEM (128 columns)
-//   softmax row-wise              one query row per thread (tcgen05.ld 32x32b): no shuffles; exp2 with log2e-prescale
+//   softmax row-wise              two threads per query row (64 key columns each; warps w and w+4 share a TMEM lane
+//                                 quadrant), row maximum exchanged through smem; exp2 with log2e-prescale
 //   O[128x64] += P.V              A = P (bf16, smem, K-major over keys), B = V tile (MN-major view of the [key][d] tile)
 // O lives in TMEM and is rescaled in place when the running maximum moves.  K/V tiles are double-buffered by TMA.
-// 112 KB smem + 256 TMEM columns per CTA -> two CTAs per SM overlap each other's MMA and softmax phases.
+// 112 KB smem + 256 TMEM columns per CTA -> two CTAs (16 warps) per SM overlap each other's MMA and softmax phases.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -23,14 +24,14 @@
 namespace tb {
 namespace attn {
 
-constexpr int D = 64, BM = 128, BN = 128, NT = 128;
+constexpr int D = 64, BM = 128, BN = 128, NT = 256;
 constexpr uint32_t SM_Q = 0;                  // [128][64]           16 KB
 constexpr uint32_t SM_K = 16384;              // 2 x [128][64]       32 KB
 constexpr uint32_t SM_V = SM_K + 32768;       // 2 x [128][64]       32 KB
 constexpr uint32_t SM_P = SM_V + 32768;       // 2 blocks [128][64]  32 KB  (keys 0-63 | 64-127)
 constexpr uint32_t SM_MISC = SM_P + 32768;    // barriers
 constexpr uint32_t SM_TOTAL = SM_MISC + 256;
-constexpr uint32_t TM_S = 0, TM_O = 128;
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_X = 192;  // TM_X + ch: scalar exchange cells of the two threads of a row
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
@@ -51,7 +52,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 int T, int H, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane;  // query row of this thread == TMEM lane
+  const int ch = warp >> 2;                // which 64 key columns of the S tile / which 32 columns of O
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   // No out-of-bounds TMA boxes: the last query / key tile is shifted back to end exactly at T (T >= 128 is required);
   // rows it shares with the previous tile are masked (keys) or recomputed identically (queries).
@@ -76,7 +79,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+  const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, 16384);
@@ -117,51 +120,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---- online softmax for this thread's query row
     const int kbase = min(j * BN, T - BN);
     const int first_new = j * BN - kbase;  // keys below this index were already consumed by the previous tile
-    float mx = m_run;
+    // (only a shifted-back tail tile needs the key masks; the row maximum is taken on the raw scores, scale > 0)
+    float mraw = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float s[32];
-      tmem_ld32(tmem + lane_addr + TM_S + 32 * c, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(tmem + lane_addr + TM_S + 64 * ch + 32 * c, reinterpret_cast<uint32_t*>(s));
       tc_wait_ld();
+      if (first_new == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float v = (32 * c + i >= first_new) ? s[i] * scale_log2 : -INFINITY;
-        mx = fmaxf(mx, v);
+        for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, s[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, (64 * ch + 32 * c + i >= first_new) ? s[i] : -INFINITY);
       }
     }
+    // the two threads of a row sit on the same TMEM lane: exchange the partial maxima through two spare TMEM cells
+    tmem_st1(tmem + lane_addr + TM_X + ch, __float_as_uint(mraw));
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    {
+      const uint32_t other = tmem_ld1(tmem + lane_addr + TM_X + (ch ^ 1));
+      tc_wait_ld();
+      mraw = fmaxf(mraw, __uint_as_float(other));
+    }
+    const float mx = fmaxf(m_run, mraw * scale_log2);
     const float alpha = ex2(m_run - mx);  // m_run = -inf on the first tile -> alpha = 0 (O, l start at 0 anyway)
     float lsum = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float s[32];
-      tmem_ld32(tmem + lane_addr + TM_S + 32 * c, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(tmem + lane_addr + TM_S + 64 * ch + 32 * c, reinterpret_cast<uint32_t*>(s));
       tc_wait_ld();
+      if (first_new == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float pexp = (32 * c + i >= first_new) ? ex2(fmaf(s[i], scale_log2, -mx)) : 0.f;
-        lsum += pexp;
-        s[i] = pexp;
+        for (int i = 0; i < 32; ++i) {
+          s[i] = ex2(fmaf(s[i], scale_log2, -mx));
+          lsum += s[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s[i] = (64 * ch + 32 * c + i >= first_new) ? ex2(fmaf(s[i], scale_log2, -mx)) : 0.f;
+          lsum += s[i];
+        }
       }
-      // P chunk -> smem (A operand, K-major over keys): block (c >> 1), 16-byte chunks 4*(c&1) .. +3 of row tid
+      // P chunk -> smem (A operand, K-major over keys): block ch, 16-byte chunks 4*c .. +3 of this row
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        st_shared_v4(sbase + SM_P + (c >> 1) * 16384 + sw128_off(tid, 4 * (c & 1) + q), pack_bf16(s[8 * q], s[8 * q + 1]),
+        st_shared_v4(sbase + SM_P + ch * 16384 + sw128_off(row, 4 * c + q), pack_bf16(s[8 * q], s[8 * q + 1]),
                      pack_bf16(s[8 * q + 2], s[8 * q + 3]), pack_bf16(s[8 * q + 4], s[8 * q + 5]), pack_bf16(s[8 * q + 6], s[8 * q + 7]));
     }
-    l_run = fmaf(l_run, alpha, lsum);
-    m_run = mx;
-    if (j > 0) {  // rescale the running output (the PV MMA of tile j-1 has completed: its commit was waited below)
+    l_run = fmaf(l_run, alpha, lsum);  // partial row sum over this thread's key columns (combined in the epilogue)
+    // rescale the running output (this thread: 32 of the 64 columns) only when some row of this warp moved its maximum
+    // (the PV MMA of tile j-1 has completed: its commit was waited below); after the first tiles the maximum rarely moves
+    if (j > 0 && __any_sync(0xffffffffu, mx > m_run)) {
+      float o[32];
+      tmem_ld32(tmem + lane_addr + TM_O + 32 * ch, reinterpret_cast<uint32_t*>(o));
+      tc_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float o[32];
-        tmem_ld32(tmem + lane_addr + TM_O + 32 * c, reinterpret_cast<uint32_t*>(o));
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= alpha;
-        tmem_st32(tmem + lane_addr + TM_O + 32 * c, reinterpret_cast<uint32_t*>(o));
-      }
+      for (int i = 0; i < 32; ++i) o[i] *= alpha;
+      tmem_st32(tmem + lane_addr + TM_O + 32 * ch, reinterpret_cast<uint32_t*>(o));
       tc_wait_st();
     }
+    m_run = mx;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -182,23 +206,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
   }
 
-  // ---- epilogue: O / l -> bf16 -> out[b, q0 + tid, h, :]
+  // ---- epilogue: O / l -> bf16 -> out[b, q0 + row, h, 32 ch .. 32 ch + 31]
   {
-    const float inv = 1.f / l_run;
+    tmem_st1(tmem + lane_addr + TM_X + 2 + ch, __float_as_uint(l_run));  // combine the two partial row sums
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t l_other = tmem_ld1(tmem + lane_addr + TM_X + 2 + (ch ^ 1));
+    tc_wait_ld();
+    const float l_tot = l_run + __uint_as_float(l_other);
+    const float inv = 1.f / l_tot;
     // row statistic for the backward (attn_bwd.cu): log2-domain log-sum-exp, P = exp2(S * scale_log2 - lse2)
-    if (lse2) lse2[((size_t)b * H + h) * T + q0 + tid] = m_run + log2f(l_run);
-    __nv_bfloat16* og = Out + (((size_t)b * T + q0 + tid) * H + h) * D;
+    if (lse2 && ch == 0) lse2[((size_t)b * H + h) * T + q0 + row] = m_run + log2f(l_tot);
+    __nv_bfloat16* og = Out + (((size_t)b * T + q0 + row) * H + h) * D + 32 * ch;
+    float o[32];
+    tmem_ld32(tmem + lane_addr + TM_O + 32 * ch, reinterpret_cast<uint32_t*>(o));
+    tc_wait_ld();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float o[32];
-      tmem_ld32(tmem + lane_addr + TM_O + 32 * c, reinterpret_cast<uint32_t*>(o));
-      tc_wait_ld();
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(og + 32 * c + 8 * q) =
-            make_uint4(pack_bf16(o[8 * q] * inv, o[8 * q + 1] * inv), pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv),
-                       pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv), pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv));
-    }
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(og + 8 * q) =
+          make_uint4(pack_bf16(o[8 * q] * inv, o[8 * q + 1] * inv), pack_bf16(o[8 * q + 2] * inv, o[8 * q + 3] * inv),
+                     pack_bf16(o[8 * q + 4] * inv, o[8 * q + 5] * inv), pack_bf16(o[8 * q + 6] * inv, o[8 * q + 7] * inv));
   }
   tc_fence_before();
   __syncthreads();
