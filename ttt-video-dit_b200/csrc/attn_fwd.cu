@@ -236,8 +236,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace attn
 
-// 4-D bf16 tensor [B][T][H][64] (innermost first: {64, H, T, B}), box {64, 1, 128, 1}, 128-B swizzle
-int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H) {
+// 4-D bf16 tensor [B][T][H][64] (innermost first: {64, H, T, B}), box {64, 1, box_rows, 1}, 128-B swizzle
+int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H, int box_rows) {
   static thread_local char detail[160];
   void* ptr = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -246,7 +246,7 @@ int make_bthd_tmap(CUtensorMap* tm, const void* base, int B, int T, int H) {
   PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(ptr);
   cuuint64_t gdim[4] = {64, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t gstride[3] = {128, (cuuint64_t)H * 128, (cuuint64_t)T * H * 128};
-  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -263,7 +263,7 @@ cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V
                                      int H, float scale, cudaStream_t stream) {
   if (B <= 0 || T < attn::BM || H <= 0) { g_where = "bad sizes (T must be >= 128)"; return cudaErrorInvalidValue; }
   CUtensorMap tq, tk, tv;
-  if (make_bthd_tmap(&tq, Q, B, T, H) || make_bthd_tmap(&tk, K, B, T, H) || make_bthd_tmap(&tv, V, B, T, H))
+  if (make_bthd_tmap(&tq, Q, B, T, H, 128) || make_bthd_tmap(&tk, K, B, T, H, 128) || make_bthd_tmap(&tv, V, B, T, H, 128))
     return cudaErrorInvalidValue;
   static bool attr_done = false;
   if (!attr_done) {
