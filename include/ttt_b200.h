@@ -96,6 +96,19 @@ int ttt_b200_attention_backward(const void* q, const void* k, const void* v, con
                                 const float* lse2, float* delta_scratch, void* dq, void* dk, void* dv, int B, int T, int H,
                                 float scale, void* stream);
 
+/* Input preparation of the TTT op after the q/k/v Linears.  Replaces the torch-op chain of
+ * TTTBase.process_input, ttt/models/ssm/ttt_layer.py:252-306: L2-normalise q,k (:265-266), RoPE with global positions on
+ * the video tokens (:271-276), reconstruction target XV <- LN(XV - XK)*gamma + beta + XK (:219-235), transpose to
+ * mini-batches (:237-250), multi-scene interleave (:157-189) and eta (:143-155,287-288).
+ * xq/xk/xv: bf16 [B,L,H*64] (outputs of wq/wk/wv); lr_logit: f32 [B,L,H] = X.w_h + b_h; rope_cos/rope_sin: f32 [Lv,32]
+ * (angle per video position and feature pair, ssm/utils.py:9-53); ln_weight/ln_bias: f32 [H,64]; interleave_index: int32 [L]
+ * source token of every destination token, or NULL for a single scene.  Outputs: XQ/XK/XV bf16 [B,H,L/CS,CS,64],
+ * last_eta bf16 [B,H,L/CS,CS] = the one eta row the scan reads (the reference materialises [B,H,NC,CS,CS]). */
+int ttt_b200_process_input(const void* xq, const void* xk, const void* xv, const float* lr_logit, const float* rope_cos,
+                           const float* rope_sin, const float* ln_weight, const float* ln_bias, const int* interleave_index,
+                           void* XQ, void* XK, void* XV, void* last_eta, int B, int L, int H, int seq_text_length,
+                           int mini_batch_size, float ttt_base_lr, void* stream);
+
 /* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
  * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in
  * ttt/models/cogvideo/dit.py:90-103,213-222,241-266.  Tensors are bf16 [B, L, E], text tokens first

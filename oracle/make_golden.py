@@ -151,10 +151,61 @@ def gen_block():
                os.path.join(GOLD, "seq_block_ref.pt"))
 
 
+def gen_process_input():
+    """TTTBase.process_input (ttt_layer.py:252-306) through the reference's own module, single- and multi-scene."""
+    from ttt.models.cogvideo.utils import SequenceMetadata
+    from ttt.models.configs import ModelConfig
+    from ttt.models.ssm.ttt_layer import TTTLinear
+    from ttt.models.ssm.utils import precompute_freqs_cis_3d
+
+    torch.manual_seed(0)
+    out = []
+    for (frames, TL, chunks) in ((13, 16, 1), (25, 8, 2)):
+        E, NH, Hh, Ww, CS = 128, 2, 4, 4, 16
+        cfg = ModelConfig(model_dim=E, num_heads=NH, num_layers=1, ssm_layer="ttt_linear", mini_batch_size=CS,
+                          ttt_base_lr=1.0, latent_height=Hh, latent_width=Ww, compressed_num_frames=frames, adapter_method="sft")
+        m = TTTLinear(cfg, use_kernel=False).double()
+        with torch.no_grad():
+            for n, p_ in m.named_parameters():
+                p_.copy_(torch.randn_like(p_) * (0.3 if p_.dim() <= 2 and "ttt_norm" in n else 0.08))
+            m.ttt_norm_weight.add_(1.0)
+        tpf = Hh * Ww
+        md = SequenceMetadata(text_length=TL, seq_text_length=TL * chunks, num_frames=frames, num_chunks=chunks,
+                              tokens_per_frame=tpf, latent_height=Hh, latent_width=Ww, t_emb=torch.zeros(1, 8))
+        if chunks > 1:
+            md.init_multiscene_offsets()
+        B, L = 2, TL * chunks + frames * tpf
+        assert L % CS == 0
+        X = torch.randn(B, L, E, dtype=torch.float64)
+        fc = precompute_freqs_cis_3d(E // NH, Hh, Ww, frames)
+        with torch.no_grad():
+            ref = m.process_input(X, fc, md)
+            q0, k0, v0 = (lin(X).reshape(B, L, NH, E // NH) for lin in (m.wq, m.wk, m.wv))
+            logit = torch.einsum("blc,hdc->blh", X, m.learnable_ttt_lr_weight) + m.learnable_ttt_lr_bias.reshape(1, 1, -1)
+        cos, sin = O.ttt_rope_tables(Hh, Ww, frames, E // NH)
+        assert torch.allclose(torch.complex(cos, sin), fc, atol=1e-6)
+        idx = O.interleave_index(L, TL, chunks, md.init_offset) if chunks > 1 else None
+        mine = O.ttt_process_input(q0, k0, v0, logit, cos.double(), sin.double(), m.ttt_norm_weight.detach(),
+                                   m.ttt_norm_bias.detach(), TL * chunks, cfg.ttt_base_lr, CS, idx)
+        for a, n in zip(mine, ("XQ", "XK", "XV", "eta")):
+            assert O.rel_err(a, ref[n]) < 1e-6, (n, O.rel_err(a, ref[n]))
+        out.append(dict(cfg=dict(E=E, NH=NH, Hh=Hh, Ww=Ww, frames=frames, TL=TL, chunks=chunks, CS=CS, B=B, L=L,
+                                 base_lr=cfg.ttt_base_lr, init_offset=md.init_offset),
+                        q0=q0.float(), k0=k0.float(), v0=v0.float(), logit=logit.float(),
+                        ln_w=m.ttt_norm_weight.detach().float(), ln_b=m.ttt_norm_bias.detach().float(),
+                        ref={n: ref[n].float() for n in ("XQ", "XK", "XV")}, ref_last_eta=ref["eta"][:, :, :, -1, :].float()))
+    print("process_input ok")
+    torch.save(out, os.path.join(GOLD, "process_input_ref.pt"))
+
+
 if __name__ == "__main__":
     assert os.path.isdir("/root/reference/ttt"), "the reference is only present in the build container"
+    if len(sys.argv) > 1 and sys.argv[1] == "process_input":
+        gen_process_input()
+        sys.exit(0)
     gen_mlp()
     gen_linear()
     gen_block()
+    gen_process_input()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

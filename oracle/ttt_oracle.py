@@ -552,3 +552,67 @@ def local_attention_block(vid, text, P, num_heads, text_length, tokens_per_frame
         out_vid[:, s:e] += a[:, text_length:]
         cnt[:, s:e] += 1
     return torch.cat((out_txt, out_vid / cnt), dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# TTTBase.process_input (ttt/models/ssm/ttt_layer.py:252-306) without the q/k/v Linears: the op's input preparation
+# --------------------------------------------------------------------------------------
+def ttt_rope_tables(height, width, num_frames, head_dim, theta=10000.0):
+    """ssm/utils.py:9-53 (precompute_freqs_cis_3d): angle per (video position, pair) -> (cos, sin) [(t h w), head_dim/2]."""
+    dim_t = head_dim // 4
+    dim_h = head_dim // 8 * 3
+    dim_w = head_dim // 8 * 3
+    f_t = 1.0 / (theta ** (torch.arange(0, dim_t, 2)[: dim_t // 2].float() / dim_t))
+    f_h = 1.0 / (theta ** (torch.arange(0, dim_h, 2)[: dim_h // 2].float() / dim_h))
+    f_w = 1.0 / (theta ** (torch.arange(0, dim_w, 2)[: dim_w // 2].float() / dim_w))
+    g_t = torch.arange(num_frames, dtype=torch.float32)[:, None] * f_t[None]
+    g_h = torch.arange(height, dtype=torch.float32)[:, None] * f_h[None]
+    g_w = torch.arange(width, dtype=torch.float32)[:, None] * f_w[None]
+    T, Hh, Ww = num_frames, height, width
+    ang = torch.cat([
+        g_t[:, None, None, :].expand(T, Hh, Ww, -1),
+        g_h[None, :, None, :].expand(T, Hh, Ww, -1),
+        g_w[None, None, :, :].expand(T, Hh, Ww, -1)], dim=-1).reshape(T * Hh * Ww, -1)
+    return ang.cos(), ang.sin()
+
+
+def interleave_index(L, text_length, num_chunks, init_offset):
+    """ttt_layer.py:157-189 (interleave) as a gather index: out[:, :, l] = x[:, :, idx[l]] over the flattened token axis."""
+    seq_text = text_length * num_chunks
+    text = torch.arange(seq_text).chunk(num_chunks)
+    video = torch.arange(seq_text, L)
+    v0 = init_offset - text_length
+    vids = (video[:v0],) + tuple(video[v0:].chunk(num_chunks - 1))
+    return torch.cat([torch.cat((text[i], vids[i])) for i in range(num_chunks)])
+
+
+def ttt_process_input(XQ, XK, XV, lr_logit, cos, sin, ln_w, ln_b, seq_text_length, base_lr, CS, index=None):
+    """ttt_layer.py:252-306 after the Linears.  XQ/XK/XV [B,L,H,F] (Linear outputs), lr_logit [B,L,H] (= X.w_h + b_h,
+    ttt_layer.py:148-151), cos/sin [Lv, F/2].  Returns XQ, XK, XV [B,H,NC,CS,F] and eta [B,H,NC,CS,CS] exactly as the
+    reference builds them (eta rows are repeated BEFORE the interleave, so interleaved rows mix mini-batches)."""
+    B, L, H, Fd = XQ.shape
+    q = F.normalize(XQ, p=2, dim=-1)  # :265-266
+    k = F.normalize(XK, p=2, dim=-1)
+
+    def rope(x):  # ssm/utils.py:82-108: complex multiply on interleaved pairs, video tokens only
+        xv = x[:, seq_text_length:].reshape(B, L - seq_text_length, H, Fd // 2, 2)
+        c, s_ = cos[: L - seq_text_length, None, :].to(x.dtype), sin[: L - seq_text_length, None, :].to(x.dtype)
+        re = xv[..., 0] * c - xv[..., 1] * s_
+        im = xv[..., 0] * s_ + xv[..., 1] * c
+        return torch.cat((x[:, :seq_text_length], torch.stack((re, im), dim=-1).flatten(-2)), dim=1)
+
+    q, k = rope(q), rope(k)
+    d = XV - k  # ln_reconstruction_target :219-235 (unbiased std, eps added to std)
+    d = (d - d.mean(-1, keepdim=True)) / (d.std(-1, keepdim=True) + 1e-8)
+    v = ln_w[None, None] * d + ln_b[None, None] + k
+    NC = L // CS
+    to_mb = lambda t: t.transpose(1, 2).reshape(B, H, NC, CS, Fd)  # :237-250
+    q, k, v = to_mb(q), to_mb(k), to_mb(v)
+    lr = base_lr * torch.sigmoid(lr_logit) / Fd  # :143-155
+    lr = lr.transpose(1, 2).reshape(B, H, NC, 1, CS)
+    eta = (1.0 / CS) * lr.repeat(1, 1, 1, CS, 1)  # :287-288
+    if index is not None:  # :290-294
+        g = lambda t: t.reshape(B, H, NC * CS, -1)[:, :, index].reshape(t.shape)
+        q, k, v, eta = g(q), g(k), g(v), g(eta)
+    return q, k, v, eta
+

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 import __graft_entry__
 
 __graft_entry__.build()
-from ttt_video_dit_b200 import attention, linear_triton, seq_block
+from ttt_video_dit_b200 import attention, linear_triton, process_input, seq_block
 
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 dev = "cuda"
@@ -82,8 +82,41 @@ def bench_gate(L=18048, E=3072, B=1):
                       "frac_of_hbm_peak": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
 
 
+def bench_attention_bwd(T=18048, H=48, B=1):
+    q, k, v, go = (torch.randn(B, T, H, 64, device=dev).to(torch.bfloat16) for _ in range(4))
+    q, k, v = (t.requires_grad_(True) for t in (q, k, v))
+
+    def step():
+        attention.sdpa_bthd(q, k, v).backward(go)
+
+    ms = timeit(step, iters=5)
+    qh, kh, vh = (t.detach().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v))
+    goh = go.permute(0, 2, 1, 3)
+    ms_lib = timeit(lambda: F.scaled_dot_product_attention(qh, kh, vh, is_causal=False).backward(goh), iters=5)
+    flop = 3.5 * 4.0 * T * T * 64 * H * B  # forward 1x + backward 2.5x
+    print(json.dumps({"kernel": "attn_fwd_kernel + attn_bwd_kernel<0>,<1> (sdpa_bthd fwd+bwd)", "shape": [B, T, H, 64], "ms": ms,
+                      "tflops": flop / ms / 1e9, "frac_of_bf16_peak": flop / ms / 1e9 / peaks["bf16_tflops"],
+                      "library_sdpa_ms": ms_lib, "speed_vs_library": ms_lib / ms}))
+
+
+def bench_process_input(L=18048, H=48, B=1):
+    g = torch.Generator().manual_seed(0)
+    xq, xk, xv = (torch.randn(B, L, H * 64, generator=g).to(torch.bfloat16).to(dev) for _ in range(3))
+    logit = torch.randn(B, L, H, generator=g).to(dev)
+    cos, sin = torch.rand(L, 32, generator=g).to(dev), torch.rand(L, 32, generator=g).to(dev)
+    lw, lb = torch.ones(H, 64, device=dev), torch.zeros(H, 64, device=dev)
+    ms = timeit(lambda: process_input.prepare(xq, xk, xv, logit, cos, sin, lw, lb, 498, 64, 0.1))
+    bytes_ = 6 * xq.numel() * 2 + logit.numel() * 4 + B * H * L * 2  # read q,k,v + write XQ,XK,XV (+ logits, eta)
+    print(json.dumps({"kernel": "ttt_process_input_kernel", "shape": [B, L, H * 64], "ms": ms, "GBps": bytes_ / ms / 1e6,
+                      "frac_of_hbm_peak": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["attention", "linear", "gate"]
+    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input"]
+    if "attention_bwd" in which:
+        bench_attention_bwd()
+    if "process_input" in which:
+        bench_process_input()
     if "attention" in which:
         bench_attention()
     if "linear" in which:

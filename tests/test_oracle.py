@@ -89,3 +89,19 @@ def test_dual_equals_primal_only_for_row_uniform_eta():
     eta2[:, :, :, :32] *= 3.0  # rows differ
     e2, _ = O.ttt_mlp_eager(d["XK"], d["XQ"], d["XV"], eta2, d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"])
     assert O.rel_err(p, e2.permute(0, 3, 1, 2, 4)) > 1e-6
+
+
+def test_process_input_restatement_matches_reference_fixture():
+    """oracle.ttt_process_input == the reference's TTTBase.process_input (ttt_layer.py:252-306), single and multi scene."""
+    for fx in torch.load(os.path.join(GOLD, "process_input_ref.pt"), weights_only=False):
+        c = fx["cfg"]
+        cos, sin = O.ttt_rope_tables(c["Hh"], c["Ww"], c["frames"], c["E"] // c["NH"])
+        idx = O.interleave_index(c["L"], c["TL"], c["chunks"], c["init_offset"]) if c["chunks"] > 1 else None
+        q, k, v, eta = O.ttt_process_input(fx["q0"], fx["k0"], fx["v0"], fx["logit"], cos, sin, fx["ln_w"], fx["ln_b"],
+                                           c["TL"] * c["chunks"], c["base_lr"], c["CS"], idx)
+        for a, n in ((q, "XQ"), (k, "XK"), (v, "XV")):
+            assert O.rel_err(a, fx["ref"][n]) < 1e-5, n
+        assert O.rel_err(eta[:, :, :, -1, :], fx["ref_last_eta"]) < 1e-5
+        if idx is not None:  # the interleave makes eta rows non-uniform (SURVEY trap #1): the scan reads the LAST row
+            assert not torch.allclose(eta[:, :, :, 0, :], eta[:, :, :, -1, :])
+

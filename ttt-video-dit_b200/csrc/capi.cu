@@ -163,6 +163,19 @@ int ttt_b200_attention_backward(const void* q, const void* k, const void* v, con
                   "ttt_b200_attention_backward");
 }
 
+int ttt_b200_process_input(const void* xq, const void* xk, const void* xv, const float* lr_logit, const float* rope_cos,
+                           const float* rope_sin, const float* ln_weight, const float* ln_bias, const int* interleave_index,
+                           void* XQ, void* XK, void* XV, void* last_eta, int B, int L, int H, int seq_text_length,
+                           int mini_batch_size, float ttt_base_lr, void* stream) {
+  if (!xq || !xk || !xv || !lr_logit || !rope_cos || !rope_sin || !ln_weight || !ln_bias || !XQ || !XK || !XV || !last_eta)
+    return fail(-1, "ttt_b200_process_input: null pointer argument");
+  if (int rc = bind_device(xq)) return rc;
+  return cuda_ret(tb::launch_process_input(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_weight, ln_bias, interleave_index, XQ,
+                                           XK, XV, last_eta, B, L, H, seq_text_length, mini_batch_size, ttt_base_lr,
+                                           (cudaStream_t)stream),
+                  "ttt_b200_process_input");
+}
+
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");

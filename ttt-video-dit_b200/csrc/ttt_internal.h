@@ -96,3 +96,10 @@ namespace tb {
 cudaError_t launch_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
                               long long sink_floats, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_process_input(const void* xq, const void* xk, const void* xv, const float* lr_logit, const float* cosT,
+                                 const float* sinT, const float* ln_w, const float* ln_b, const int* index, void* XQ,
+                                 void* XK, void* XV, void* last_eta, int B, int L, int H, int seq_text_length, int mini_batch,
+                                 float base_lr, cudaStream_t stream);
+}  // namespace tb

@@ -1,0 +1,50 @@
+"""Input preparation of the TTT op on libttt_b200.so: mirror of ``TTTBase.process_input``
+(reference: ttt/models/ssm/ttt_layer.py:252-306).  The q/k/v Linears and the lr projection stay library GEMMs; everything
+between them and the scan (L2 norm, RoPE, reconstruction target, mini-batch transpose, interleave, eta) is one kernel
+(csrc/process_input.cu).  Forward only (sampling path); there is no eager fallback."""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def prepare(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_length, mini_batch_size, ttt_base_lr, index=None):
+    """xq/xk/xv bf16 [B,L,H*64]; lr_logit [B,L,H]; rope_cos/sin [Lv,32]; index: int32 [L] gather index of the multi-scene
+    interleave (None for one scene).  Returns XQ, XK, XV bf16 [B,H,NC,CS,64] and last_eta bf16 [B,H,NC,CS]."""
+    B, L, E = xq.shape
+    H = E // 64
+    if E != H * 64 or L % mini_batch_size:
+        raise RuntimeError("process_input: model_dim must be heads x 64 and L a multiple of the mini-batch size")
+    for t, n in ((xq, "xq"), (xk, "xk"), (xv, "xv")):
+        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == xq.shape):
+            raise RuntimeError(f"{n} must be a contiguous CUDA bf16 tensor [B, L, H*64]")
+    dev = xq.device
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    lg, c, s, lw, lb = f32(lr_logit), f32(rope_cos), f32(rope_sin), f32(ln_w).reshape(H, 64), f32(ln_b).reshape(H, 64)
+    if lg.shape != (B, L, H) or c.shape[-1] != 32 or c.shape[0] < L - seq_text_length:
+        raise RuntimeError("process_input: lr_logit must be [B,L,H] and the RoPE tables [>= video tokens, 32]")
+    idx = None if index is None else index.to(device=dev, dtype=torch.int32).contiguous()
+    NC = L // mini_batch_size
+    XQ = torch.empty(B, H, NC, mini_batch_size, 64, device=dev, dtype=torch.bfloat16)
+    XK, XV = torch.empty_like(XQ), torch.empty_like(XQ)
+    eta = torch.empty(B, H, NC, mini_batch_size, device=dev, dtype=torch.bfloat16)
+    p = _lib.ptr
+    code = _lib.lib().ttt_b200_process_input(p(xq), p(xk), p(xv), p(lg), p(c), p(s), p(lw), p(lb), p(idx), p(XQ), p(XK), p(XV),
+                                             p(eta), B, L, H, int(seq_text_length), int(mini_batch_size), float(ttt_base_lr),
+                                             _lib.current_stream())
+    _lib.check(code, "ttt_b200_process_input")
+    return XQ, XK, XV, eta
+
+
+def process_input(hidden_states, P, rope_cos, rope_sin, seq_text_length, mini_batch_size, ttt_base_lr, index=None):
+    """``TTTBase.process_input`` (ttt_layer.py:252-306).  P: dict with wq/wk/wv ``.weight``/``.bias``,
+    ``learnable_ttt_lr_weight`` [H,1,E], ``learnable_ttt_lr_bias`` [H,1], ``ttt_norm_weight``/``ttt_norm_bias`` [H,64].
+    Returns {"XQ","XK","XV"} [B,H,NC,CS,64] and "last_eta" [B,H,NC,CS]."""
+    xq = F.linear(hidden_states, P["wq.weight"], P["wq.bias"]).contiguous()
+    xk = F.linear(hidden_states, P["wk.weight"], P["wk.bias"]).contiguous()
+    xv = F.linear(hidden_states, P["wv.weight"], P["wv.bias"]).contiguous()
+    H = P["learnable_ttt_lr_weight"].shape[0]
+    logit = F.linear(hidden_states, P["learnable_ttt_lr_weight"].reshape(H, -1), P["learnable_ttt_lr_bias"].reshape(H))
+    XQ, XK, XV, eta = prepare(xq, xk, xv, logit, rope_cos, rope_sin, P["ttt_norm_weight"], P["ttt_norm_bias"], seq_text_length,
+                              mini_batch_size, ttt_base_lr, index)
+    return {"XQ": XQ, "XK": XK, "XV": XV, "last_eta": eta}
