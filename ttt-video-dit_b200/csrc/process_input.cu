@@ -8,9 +8,10 @@
 // BEFORE interleaving, so the last row of an interleaved mini-batch n is the lr vector of the SOURCE mini-batch that holds
 // the source token of position n*CS + CS-1 -- reproduced here so that the op sees exactly the reference's numbers.
 //
-// One warp per (token, head) row: lane = one interleaved RoPE pair (2 of the 64 features), row reductions by shuffles;
-// a CTA = 8 consecutive destination tokens of one head, so the [B,H,L,F] stores are 1 KB contiguous.  HBM-bound:
-// 3 x 128 B in + 3 x 128 B out per row.
+// Half a warp per (token, head) row: lane = two interleaved RoPE pairs (4 of the 64 features, one 8-byte load per tensor),
+// row reductions by 4 shuffles; every warp handles 4 rows and issues all of its loads before the first reduction (enough
+// bytes in flight to cover the HBM latency); a CTA = 32 consecutive destination tokens of one head, so the [B,H,L,F]
+// stores are 4 KB contiguous.  HBM-bound: 3 x 128 B in + 3 x 128 B out per row.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,52 +21,84 @@
 
 namespace tb {
 
-__device__ __forceinline__ float warp_sum(float v) {
+__device__ __forceinline__ float half_warp_sum(float v) {  // over the 16 lanes that share a row
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  for (int m = 8; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
 }
 
 __global__ void __launch_bounds__(256)
-ttt_process_input_kernel(const uint32_t* __restrict__ xq, const uint32_t* __restrict__ xk, const uint32_t* __restrict__ xv,
-                         const float* __restrict__ lr_logit, const float* __restrict__ cosT, const float* __restrict__ sinT,
+ttt_process_input_kernel(const uint2* __restrict__ xq, const uint2* __restrict__ xk, const uint2* __restrict__ xv,
+                         const float* __restrict__ lr_logit, const float2* __restrict__ cosT, const float2* __restrict__ sinT,
                          const float* __restrict__ ln_w, const float* __restrict__ ln_b, const int* __restrict__ index,
-                         uint32_t* __restrict__ oq, uint32_t* __restrict__ ok, uint32_t* __restrict__ ov,
+                         uint2* __restrict__ oq, uint2* __restrict__ ok, uint2* __restrict__ ov,
                          __nv_bfloat16* __restrict__ oeta, int L, int H, int seq_text, int CS, float eta_scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l = blockIdx.x * 8 + warp, h = blockIdx.y, b = blockIdx.z;
-  if (l >= L) return;
-  const int src = index ? index[l] : l;
-  const size_t in = (((size_t)b * L + src) * H + h) * 32 + lane;
-  const uint32_t qp = xq[in], kp = xk[in], vp = xv[in];
-  float q0 = bf16_lo(qp), q1 = bf16_hi(qp), k0 = bf16_lo(kp), k1 = bf16_hi(kp), v0 = bf16_lo(vp), v1 = bf16_hi(vp);
-  const float qn = 1.f / fmaxf(sqrtf(warp_sum(q0 * q0 + q1 * q1)), 1e-12f);  // F.normalize eps
-  const float kn = 1.f / fmaxf(sqrtf(warp_sum(k0 * k0 + k1 * k1)), 1e-12f);
-  q0 *= qn; q1 *= qn; k0 *= kn; k1 *= kn;
-  if (src >= seq_text) {  // video token: rotate the pair by the angle of its global video position
-    const float c = cosT[(size_t)(src - seq_text) * 32 + lane], s = sinT[(size_t)(src - seq_text) * 32 + lane];
-    const float a = q0 * c - q1 * s, bq = q0 * s + q1 * c;
-    q0 = a; q1 = bq;
-    const float e = k0 * c - k1 * s, f = k0 * s + k1 * c;
-    k0 = e; k1 = f;
+  const int c = lane & 15, sub = lane >> 4;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int l0 = blockIdx.x * 32 + warp * 4;
+  int src[2];
+  uint2 qp[2], kp[2], vp[2];
+  float2 cs[2][2];  // [row][cos | sin] of this lane's two pairs
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {  // all loads first
+    const int l = min(l0 + 2 * it + sub, L - 1);
+    src[it] = index ? index[l] : l;
+    const size_t in = (((size_t)b * L + src[it]) * H + h) * 16 + c;
+    qp[it] = xq[in]; kp[it] = xk[in]; vp[it] = xv[in];
+    if (src[it] >= seq_text) {
+      cs[it][0] = cosT[(size_t)(src[it] - seq_text) * 16 + c];
+      cs[it][1] = sinT[(size_t)(src[it] - seq_text) * 16 + c];
+    } else {
+      cs[it][0] = make_float2(1.f, 1.f);  // text token: identity rotation
+      cs[it][1] = make_float2(0.f, 0.f);
+    }
   }
-  // reconstruction target: LayerNorm with the unbiased std of (XV - XK), eps added to the std
-  float d0 = v0 - k0, d1 = v1 - k1;
-  const float mean = warp_sum(d0 + d1) * (1.f / 64.f);
-  d0 -= mean; d1 -= mean;
-  const float inv = 1.f / (sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 63.f)) + 1e-8f);
-  v0 = fmaf(ln_w[h * 64 + 2 * lane], d0 * inv, ln_b[h * 64 + 2 * lane]) + k0;
-  v1 = fmaf(ln_w[h * 64 + 2 * lane + 1], d1 * inv, ln_b[h * 64 + 2 * lane + 1]) + k1;
-  const size_t out = (((size_t)b * H + h) * L + l) * 32 + lane;
-  oq[out] = pack_bf16(q0, q1);
-  ok[out] = pack_bf16(k0, k1);
-  ov[out] = pack_bf16(v0, v1);
-  if (lane == 0) {  // eta of (mini-batch n, column j): lr of token j of the source mini-batch of this mini-batch's last row
-    const int n = l / CS, j = l - n * CS;
-    const int last = n * CS + CS - 1;
-    const int src_mb = (index ? index[last] : last) / CS;
-    const float z = lr_logit[((size_t)b * L + (size_t)src_mb * CS + j) * H + h];
-    oeta[((size_t)b * H + h) * L + l] = __float2bfloat16(eta_scale / (1.f + __expf(-z)));
+  const float4 gw = *reinterpret_cast<const float4*>(ln_w + h * 64 + 4 * c);
+  const float4 gb = *reinterpret_cast<const float4*>(ln_b + h * 64 + 4 * c);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int l = l0 + 2 * it + sub;
+    float q0 = bf16_lo(qp[it].x), q1 = bf16_hi(qp[it].x), q2 = bf16_lo(qp[it].y), q3 = bf16_hi(qp[it].y);
+    float k0 = bf16_lo(kp[it].x), k1 = bf16_hi(kp[it].x), k2 = bf16_lo(kp[it].y), k3 = bf16_hi(kp[it].y);
+    float v0 = bf16_lo(vp[it].x), v1 = bf16_hi(vp[it].x), v2 = bf16_lo(vp[it].y), v3 = bf16_hi(vp[it].y);
+    const float qn = 1.f / fmaxf(sqrtf(half_warp_sum(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3)), 1e-12f);  // F.normalize eps
+    const float kn = 1.f / fmaxf(sqrtf(half_warp_sum(k0 * k0 + k1 * k1 + k2 * k2 + k3 * k3)), 1e-12f);
+    q0 *= qn; q1 *= qn; q2 *= qn; q3 *= qn;
+    k0 *= kn; k1 *= kn; k2 *= kn; k3 *= kn;
+    {  // rotate each interleaved pair by the angle of the token's global video position (identity for text tokens)
+      const float2 co = cs[it][0], si = cs[it][1];
+      float a = q0 * co.x - q1 * si.x, bb = q0 * si.x + q1 * co.x;
+      q0 = a; q1 = bb;
+      a = q2 * co.y - q3 * si.y; bb = q2 * si.y + q3 * co.y;
+      q2 = a; q3 = bb;
+      a = k0 * co.x - k1 * si.x; bb = k0 * si.x + k1 * co.x;
+      k0 = a; k1 = bb;
+      a = k2 * co.y - k3 * si.y; bb = k2 * si.y + k3 * co.y;
+      k2 = a; k3 = bb;
+    }
+    // reconstruction target: LayerNorm with the unbiased std of (XV - XK), eps added to the std
+    float d0 = v0 - k0, d1 = v1 - k1, d2 = v2 - k2, d3 = v3 - k3;
+    const float mean = half_warp_sum((d0 + d1) + (d2 + d3)) * (1.f / 64.f);
+    d0 -= mean; d1 -= mean; d2 -= mean; d3 -= mean;
+    const float inv = 1.f / (sqrtf(half_warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 63.f)) + 1e-8f);
+    v0 = fmaf(gw.x, d0 * inv, gb.x) + k0;
+    v1 = fmaf(gw.y, d1 * inv, gb.y) + k1;
+    v2 = fmaf(gw.z, d2 * inv, gb.z) + k2;
+    v3 = fmaf(gw.w, d3 * inv, gb.w) + k3;
+    if (l < L) {
+      const size_t out = (((size_t)b * H + h) * L + l) * 16 + c;
+      oq[out] = make_uint2(pack_bf16(q0, q1), pack_bf16(q2, q3));
+      ok[out] = make_uint2(pack_bf16(k0, k1), pack_bf16(k2, k3));
+      ov[out] = make_uint2(pack_bf16(v0, v1), pack_bf16(v2, v3));
+      if (c == 0) {  // eta of (mini-batch n, column j): lr of token j of the source mini-batch of this mini-batch's last row
+        const int n = l / CS, j = l - n * CS;
+        const int last = n * CS + CS - 1;
+        const int src_mb = (index ? index[last] : last) / CS;
+        const float z = lr_logit[((size_t)b * L + (size_t)src_mb * CS + j) * H + h];
+        oeta[((size_t)b * H + h) * L + l] = __float2bfloat16(eta_scale / (1.f + __expf(-z)));
+      }
+    }
   }
 }
 
@@ -78,11 +111,12 @@ cudaError_t launch_process_input(const void* xq, const void* xk, const void* xv,
     return cudaErrorInvalidValue;
   }
   g_where = "process_input launch";
-  dim3 grid((L + 7) / 8, H, B);
+  dim3 grid((L + 31) / 32, H, B);
   ttt_process_input_kernel<<<grid, 256, 0, stream>>>(
-      reinterpret_cast<const uint32_t*>(xq), reinterpret_cast<const uint32_t*>(xk), reinterpret_cast<const uint32_t*>(xv),
-      lr_logit, cosT, sinT, ln_w, ln_b, index, reinterpret_cast<uint32_t*>(XQ), reinterpret_cast<uint32_t*>(XK),
-      reinterpret_cast<uint32_t*>(XV), reinterpret_cast<__nv_bfloat16*>(last_eta), L, H, seq_text_length, mini_batch,
+      reinterpret_cast<const uint2*>(xq), reinterpret_cast<const uint2*>(xk), reinterpret_cast<const uint2*>(xv), lr_logit,
+      reinterpret_cast<const float2*>(cosT), reinterpret_cast<const float2*>(sinT), ln_w, ln_b, index,
+      reinterpret_cast<uint2*>(XQ), reinterpret_cast<uint2*>(XK), reinterpret_cast<uint2*>(XV),
+      reinterpret_cast<__nv_bfloat16*>(last_eta), L, H, seq_text_length, mini_batch,
       base_lr / 64.f / (float)mini_batch);
   return cudaGetLastError();
 }
