@@ -109,6 +109,16 @@ int ttt_b200_process_input(const void* xq, const void* xk, const void* xv, const
                            void* XQ, void* XK, void* XV, void* last_eta, int B, int L, int H, int seq_text_length,
                            int mini_batch_size, float ttt_base_lr, void* stream);
 
+/* Backward of ttt_b200_process_input (what autograd computes through ttt_layer.py:252-306).  dXQ/dXK/dXV bf16
+ * [B,H,L/CS,CS,64], d_last_eta f32 [B,H,L/CS,CS]; outputs dxq/dxk/dxv bf16 [B,L,H*64], d_lr_logit f32 [B,L,H],
+ * d_ln_weight / d_ln_bias f32 [H,64] (all overwritten). */
+int ttt_b200_process_input_backward(const void* xq, const void* xk, const void* xv, const float* lr_logit,
+                                    const float* rope_cos, const float* rope_sin, const float* ln_weight,
+                                    const int* interleave_index, const void* dXQ, const void* dXK, const void* dXV,
+                                    const float* d_last_eta, void* dxq, void* dxk, void* dxv, float* d_lr_logit,
+                                    float* d_ln_weight, float* d_ln_bias, int B, int L, int H, int seq_text_length,
+                                    int mini_batch_size, float ttt_base_lr, void* stream);
+
 /* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
  * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in
  * ttt/models/cogvideo/dit.py:90-103,213-222,241-266.  Tensors are bf16 [B, L, E], text tokens first

@@ -176,6 +176,22 @@ int ttt_b200_process_input(const void* xq, const void* xk, const void* xv, const
                   "ttt_b200_process_input");
 }
 
+int ttt_b200_process_input_backward(const void* xq, const void* xk, const void* xv, const float* lr_logit,
+                                    const float* rope_cos, const float* rope_sin, const float* ln_weight,
+                                    const int* interleave_index, const void* dXQ, const void* dXK, const void* dXV,
+                                    const float* d_last_eta, void* dxq, void* dxk, void* dxv, float* d_lr_logit,
+                                    float* d_ln_weight, float* d_ln_bias, int B, int L, int H, int seq_text_length,
+                                    int mini_batch_size, float ttt_base_lr, void* stream) {
+  if (!xq || !xk || !xv || !lr_logit || !rope_cos || !rope_sin || !ln_weight || !dXQ || !dXK || !dXV || !d_last_eta || !dxq ||
+      !dxk || !dxv || !d_lr_logit || !d_ln_weight || !d_ln_bias)
+    return fail(-1, "ttt_b200_process_input_backward: null pointer argument");
+  if (int rc = bind_device(xq)) return rc;
+  return cuda_ret(tb::launch_process_input_backward(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_weight, interleave_index, dXQ,
+                                                    dXK, dXV, d_last_eta, dxq, dxk, dxv, d_lr_logit, d_ln_weight, d_ln_bias, B,
+                                                    L, H, seq_text_length, mini_batch_size, ttt_base_lr, (cudaStream_t)stream),
+                  "ttt_b200_process_input_backward");
+}
+
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");

@@ -103,3 +103,11 @@ cudaError_t launch_process_input(const void* xq, const void* xk, const void* xv,
                                  void* XK, void* XV, void* last_eta, int B, int L, int H, int seq_text_length, int mini_batch,
                                  float base_lr, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_process_input_backward(const void* xq, const void* xk, const void* xv, const float* lr_logit,
+                                          const float* cosT, const float* sinT, const float* ln_w, const int* index,
+                                          const void* gQ, const void* gK, const void* gV, const float* g_eta, void* gxq,
+                                          void* gxk, void* gxv, float* g_logit, float* g_ln_w, float* g_ln_b, int B, int L,
+                                          int H, int seq_text_length, int mini_batch, float base_lr, cudaStream_t stream);
+}  // namespace tb

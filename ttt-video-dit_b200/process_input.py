@@ -1,16 +1,14 @@
 """Input preparation of the TTT op on libttt_b200.so: mirror of ``TTTBase.process_input``
 (reference: ttt/models/ssm/ttt_layer.py:252-306).  The q/k/v Linears and the lr projection stay library GEMMs; everything
 between them and the scan (L2 norm, RoPE, reconstruction target, mini-batch transpose, interleave, eta) is one kernel
-(csrc/process_input.cu).  Forward only (sampling path); there is no eager fallback."""
+forward and one kernel backward (csrc/process_input.cu); there is no eager fallback."""
 import torch
 import torch.nn.functional as F
 
 from . import _lib
 
 
-def prepare(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_length, mini_batch_size, ttt_base_lr, index=None):
-    """xq/xk/xv bf16 [B,L,H*64]; lr_logit [B,L,H]; rope_cos/sin [Lv,32]; index: int32 [L] gather index of the multi-scene
-    interleave (None for one scene).  Returns XQ, XK, XV bf16 [B,H,NC,CS,64] and last_eta bf16 [B,H,NC,CS]."""
+def _prepare_fwd(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_length, mini_batch_size, ttt_base_lr, index=None):
     B, L, E = xq.shape
     H = E // 64
     if E != H * 64 or L % mini_batch_size:
@@ -33,7 +31,48 @@ def prepare(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_lengt
                                              p(eta), B, L, H, int(seq_text_length), int(mini_batch_size), float(ttt_base_lr),
                                              _lib.current_stream())
     _lib.check(code, "ttt_b200_process_input")
-    return XQ, XK, XV, eta
+    return (XQ, XK, XV, eta), (lg, c, s, lw, idx)
+
+
+class _Prepare(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xq, xk, xv, lr_logit, ln_w, ln_b, rope_cos, rope_sin, seq_text_length, mini_batch_size, ttt_base_lr, index):
+        outs, (lg, c, s, lw, idx) = _prepare_fwd(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_length,
+                                                 mini_batch_size, ttt_base_lr, index)
+        ctx.save_for_backward(xq, xk, xv, lg, c, s, lw, *(() if idx is None else (idx,)))
+        ctx.cfg = (int(seq_text_length), int(mini_batch_size), float(ttt_base_lr), idx is not None,
+                   lr_logit.dtype, ln_w.dtype, ln_b.dtype, ln_w.shape, ln_b.shape)
+        return outs
+
+    @staticmethod
+    def backward(ctx, gQ, gK, gV, gEta):
+        xq, xk, xv, lg, c, s, lw, *rest = ctx.saved_tensors
+        seq_text, CS, base_lr, has_idx, lg_dt, lw_dt, lb_dt, lw_shape, lb_shape = ctx.cfg
+        idx = rest[0] if has_idx else None
+        B, L, E = xq.shape
+        H = E // 64
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        gQ, gK, gV = bf(gQ), bf(gK), bf(gV)
+        ge = gEta.float().contiguous()
+        gxq, gxk, gxv = torch.empty_like(xq), torch.empty_like(xk), torch.empty_like(xv)
+        glg = torch.empty(B, L, H, device=xq.device, dtype=torch.float32)
+        glw = torch.empty(H, 64, device=xq.device, dtype=torch.float32)
+        glb = torch.empty(H, 64, device=xq.device, dtype=torch.float32)
+        p = _lib.ptr
+        code = _lib.lib().ttt_b200_process_input_backward(p(xq), p(xk), p(xv), p(lg), p(c), p(s), p(lw), p(idx), p(gQ), p(gK),
+                                                          p(gV), p(ge), p(gxq), p(gxk), p(gxv), p(glg), p(glw), p(glb), B, L, H,
+                                                          seq_text, CS, base_lr, _lib.current_stream())
+        _lib.check(code, "ttt_b200_process_input_backward")
+        return (gxq, gxk, gxv, glg.to(lg_dt), glw.reshape(lw_shape).to(lw_dt), glb.reshape(lb_shape).to(lb_dt),
+                None, None, None, None, None, None)
+
+
+def prepare(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_length, mini_batch_size, ttt_base_lr, index=None):
+    """xq/xk/xv bf16 [B,L,H*64]; lr_logit [B,L,H]; rope_cos/sin [Lv,32]; index: int32 [L] gather index of the multi-scene
+    interleave (None for one scene).  Returns XQ, XK, XV bf16 [B,H,NC,CS,64] and last_eta bf16 [B,H,NC,CS]; differentiable
+    w.r.t. xq, xk, xv, lr_logit, ln_w, ln_b."""
+    return _Prepare.apply(xq, xk, xv, lr_logit, ln_w, ln_b, rope_cos, rope_sin, seq_text_length, mini_batch_size, ttt_base_lr,
+                          index)
 
 
 def process_input(hidden_states, P, rope_cos, rope_sin, seq_text_length, mini_batch_size, ttt_base_lr, index=None):
