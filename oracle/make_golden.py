@@ -174,7 +174,7 @@ def gen_process_input():
                               tokens_per_frame=tpf, latent_height=Hh, latent_width=Ww, t_emb=torch.zeros(1, 8))
         if chunks > 1:
             md.init_multiscene_offsets()
-        B, L = 2, TL * chunks + frames * tpf
+        B, L = 1, TL * chunks + frames * tpf
         assert L % CS == 0
         X = torch.randn(B, L, E, dtype=torch.float64)
         fc = precompute_freqs_cis_3d(E // NH, Hh, Ww, frames)
@@ -189,8 +189,20 @@ def gen_process_input():
                                    m.ttt_norm_bias.detach(), TL * chunks, cfg.ttt_base_lr, CS, idx)
         for a, n in zip(mine, ("XQ", "XK", "XV", "eta")):
             assert O.rel_err(a, ref[n]) < 1e-6, (n, O.rel_err(a, ref[n]))
+        # output side (ttt_layer.py:324-331): post_norm, then undo_interleave (moved before the per-token wo Linear)
+        Oop = torch.randn(B, NH, L // CS, CS, E // NH, dtype=torch.float64)
+        with torch.no_grad():
+            pn = m.post_norm(Oop.permute(0, 2, 3, 1, 4).reshape(B, L, E))
+            ep_ref = m.undo_interleave(pn, md) if chunks > 1 else pn
+            wo_then_undo = m.undo_interleave(m.wo(pn), md) if chunks > 1 else m.wo(pn)
+            assert O.rel_err(m.wo(ep_ref), wo_then_undo) < 1e-12  # the permutation commutes with wo
+        uidx = O.undo_interleave_index(L, TL, chunks, md.init_offset, md.base_offset) if chunks > 1 else None
+        mine_ep = O.ttt_output_epilogue(Oop, m.post_norm.weight.detach(), m.post_norm.bias.detach(), 1e-6, uidx)
+        assert O.rel_err(mine_ep, ep_ref) < 1e-10, O.rel_err(mine_ep, ep_ref)
         out.append(dict(cfg=dict(E=E, NH=NH, Hh=Hh, Ww=Ww, frames=frames, TL=TL, chunks=chunks, CS=CS, B=B, L=L,
-                                 base_lr=cfg.ttt_base_lr, init_offset=md.init_offset),
+                                 base_lr=cfg.ttt_base_lr, init_offset=md.init_offset, base_offset=md.base_offset),
+                        ep_in=Oop.float(), ep_ref=ep_ref.float(), pn_w=m.post_norm.weight.detach().float(),
+                        pn_b=m.post_norm.bias.detach().float(),
                         q0=q0.float(), k0=k0.float(), v0=v0.float(), logit=logit.float(),
                         ln_w=m.ttt_norm_weight.detach().float(), ln_b=m.ttt_norm_bias.detach().float(),
                         ref={n: ref[n].float() for n in ("XQ", "XK", "XV")}, ref_last_eta=ref["eta"][:, :, :, -1, :].float()))

@@ -616,3 +616,24 @@ def ttt_process_input(XQ, XK, XV, lr_logit, cos, sin, ln_w, ln_b, seq_text_lengt
         q, k, v, eta = g(q), g(k), g(v), g(eta)
     return q, k, v, eta
 
+
+def undo_interleave_index(L, text_length, num_chunks, init_offset, base_offset):
+    """ttt_layer.py:191-217 (undo_interleave) as a gather index: out[:, m] = x[:, idx[m]]."""
+    text, vid = [], []
+    for i in range(num_chunks):
+        s0 = 0 if i == 0 else init_offset + (i - 1) * base_offset
+        e0 = init_offset if i == 0 else init_offset + i * base_offset
+        text.append(torch.arange(s0, s0 + text_length))
+        vid.append(torch.arange(s0 + text_length, e0))
+    return torch.cat(text + vid)
+
+
+def ttt_output_epilogue(O_bhncf, ln_w, ln_b, eps=1e-6, index=None):
+    """TTTMLP.ttt tail + TTTBase.forward up to (not including) wo: permute(0,2,3,1,4).reshape(B, L, E)
+    (ttt_layer.py:456,472), post_norm = LayerNorm(E, eps 1e-6) (:71,324); undo_interleave (:329-331) is a token permutation
+    and commutes with the per-token wo Linear, so it is applied here, before wo."""
+    B, H, NC, CS, Fd = O_bhncf.shape
+    x = O_bhncf.permute(0, 2, 3, 1, 4).reshape(B, NC * CS, H * Fd)
+    x = F.layer_norm(x, (H * Fd,), ln_w, ln_b, eps)
+    return x if index is None else x[:, index]
+

@@ -111,8 +111,19 @@ def bench_process_input(L=18048, H=48, B=1):
                       "frac_of_hbm_peak": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
 
 
+def bench_output_norm(L=18048, H=48, B=1):
+    x = torch.randn(B, H, L // 64, 64, 64, device=dev).to(torch.bfloat16)
+    w, b_ = torch.ones(H * 64, device=dev), torch.zeros(H * 64, device=dev)
+    ms = timeit(lambda: process_input.output_norm(x, w, b_))
+    bytes_ = 2 * x.numel() * 2
+    print(json.dumps({"kernel": "ttt_output_norm_kernel", "shape": [B, L, H * 64], "ms": ms, "GBps": bytes_ / ms / 1e6,
+                      "frac_of_hbm_peak": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input"]
+    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input", "output_norm"]
+    if "output_norm" in which:
+        bench_output_norm()
     if "attention_bwd" in which:
         bench_attention_bwd()
     if "process_input" in which:

@@ -105,3 +105,11 @@ def test_process_input_restatement_matches_reference_fixture():
         if idx is not None:  # the interleave makes eta rows non-uniform (SURVEY trap #1): the scan reads the LAST row
             assert not torch.allclose(eta[:, :, :, 0, :], eta[:, :, :, -1, :])
 
+
+def test_output_epilogue_restatement_matches_reference_fixture():
+    """oracle.ttt_output_epilogue == post_norm + undo_interleave of the reference module (ttt_layer.py:324-331)."""
+    for fx in torch.load(os.path.join(GOLD, "process_input_ref.pt"), weights_only=False):
+        c = fx["cfg"]
+        uidx = O.undo_interleave_index(c["L"], c["TL"], c["chunks"], c["init_offset"], c["base_offset"]) if c["chunks"] > 1 else None
+        assert O.rel_err(O.ttt_output_epilogue(fx["ep_in"], fx["pn_w"], fx["pn_b"], 1e-6, uidx), fx["ep_ref"]) < 1e-5
+

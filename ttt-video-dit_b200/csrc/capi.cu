@@ -192,6 +192,15 @@ int ttt_b200_process_input_backward(const void* xq, const void* xk, const void* 
                   "ttt_b200_process_input_backward");
 }
 
+int ttt_b200_output_norm(const void* op_out, const float* post_norm_weight, const float* post_norm_bias,
+                         const int* undo_interleave_index, void* out, int B, int L, int H, float eps, void* stream) {
+  if (!op_out || !post_norm_weight || !post_norm_bias || !out) return fail(-1, "ttt_b200_output_norm: null pointer argument");
+  if (int rc = bind_device(op_out)) return rc;
+  return cuda_ret(tb::launch_output_norm(op_out, post_norm_weight, post_norm_bias, undo_interleave_index, out, B, L, H, eps,
+                                         (cudaStream_t)stream),
+                  "ttt_b200_output_norm");
+}
+
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");

@@ -111,3 +111,8 @@ cudaError_t launch_process_input_backward(const void* xq, const void* xk, const 
                                           void* gxk, void* gxv, float* g_logit, float* g_ln_w, float* g_ln_b, int B, int L,
                                           int H, int seq_text_length, int mini_batch, float base_lr, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_output_norm(const void* O, const float* gamma, const float* beta, const int* index, void* out, int B, int L,
+                               int H, float eps, cudaStream_t stream);
+}  // namespace tb
