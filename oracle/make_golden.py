@@ -210,14 +210,58 @@ def gen_process_input():
     torch.save(out, os.path.join(GOLD, "process_input_ref.pt"))
 
 
+def gen_layer():
+    """Whole TTT layer forward through the reference modules in eager mode (TTTMLP / TTTLinear, use_kernel=False),
+    single scene (uniform eta rows: the eager dual form equals the kernels' last-row form, SURVEY trap #1)."""
+    from ttt.models.cogvideo.utils import SequenceMetadata
+    from ttt.models.configs import ModelConfig
+    from ttt.models.ssm.ttt_layer import TTTLinear, TTTMLP
+    from ttt.models.ssm.utils import precompute_freqs_cis_3d
+
+    torch.manual_seed(0)
+    out = []
+    for kind, cls, CS, lr in (("ttt_mlp", TTTMLP, 64, 0.1), ("ttt_linear", TTTLinear, 16, 1.0)):
+        E, NH, Hh, Ww, frames, TL = 128, 2, 4, 4, 13, 48
+        cfg = ModelConfig(model_dim=E, num_heads=NH, num_layers=1, ssm_layer=kind, mini_batch_size=CS, ttt_base_lr=lr,
+                          latent_height=Hh, latent_width=Ww, compressed_num_frames=frames, adapter_method="sft",
+                          scan_checkpoint_group_size=2)
+        m = cls(cfg, use_kernel=False).double()
+        with torch.no_grad():
+            for n, p_ in m.named_parameters():
+                if n in ("W1", "W2"):
+                    p_.copy_(torch.randn_like(p_) * 0.02)
+                elif n in ("b1", "b2"):
+                    p_.zero_()
+                else:
+                    p_.copy_(torch.randn_like(p_) * 0.08)
+            m.ttt_norm_weight.add_(1.0); m.post_norm.weight.add_(1.0)
+        tpf = Hh * Ww
+        md = SequenceMetadata(text_length=TL, seq_text_length=TL, num_frames=frames, num_chunks=1, tokens_per_frame=tpf,
+                              latent_height=Hh, latent_width=Ww, t_emb=torch.zeros(1, 8))
+        B, L = 2, TL + frames * tpf
+        assert L % CS == 0
+        X = torch.randn(B, L, E, dtype=torch.float64)
+        fc = precompute_freqs_cis_3d(E // NH, Hh, Ww, frames)
+        with torch.no_grad():
+            ref = m(X, fc, md)
+        out.append(dict(kind=kind, cfg=dict(E=E, NH=NH, Hh=Hh, Ww=Ww, frames=frames, TL=TL, CS=CS, B=B, L=L, base_lr=lr, group=2),
+                        X=X.float(), P={k: v.detach().float() for k, v in m.state_dict().items()}, ref=ref.float()))
+    print("layer ok")
+    torch.save(out, os.path.join(GOLD, "ttt_layer_ref.pt"))
+
+
 if __name__ == "__main__":
     assert os.path.isdir("/root/reference/ttt"), "the reference is only present in the build container"
     if len(sys.argv) > 1 and sys.argv[1] == "process_input":
         gen_process_input()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "layer":
+        gen_layer()
+        sys.exit(0)
     gen_mlp()
     gen_linear()
     gen_block()
     gen_process_input()
+    gen_layer()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
