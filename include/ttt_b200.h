@@ -122,9 +122,13 @@ int ttt_b200_process_input_backward(const void* xq, const void* xk, const void* 
 /* Output side of the TTT layer before wo: op_out bf16 [B,H,L/CS,CS,64] -> transpose to [B,L,H*64]
  * (ttt_layer.py:456,472), post_norm LayerNorm(H*64, eps) (ttt_layer.py:71,324) and undo_interleave (ttt_layer.py:191-217,
  * as a gather index int32 [L], NULL for a single scene; applied before the per-token wo Linear, with which it commutes).
- * out: bf16 [B,L,H*64].  Forward only. */
+ * out: bf16 [B,L,H*64].  _backward: d_out bf16 [B,L,H*64] -> d_op_out bf16 [B,H,L/CS,CS,64], d_post_norm_weight /
+ * d_post_norm_bias f32 [H*64] (overwritten). */
 int ttt_b200_output_norm(const void* op_out, const float* post_norm_weight, const float* post_norm_bias,
                          const int* undo_interleave_index, void* out, int B, int L, int H, float eps, void* stream);
+int ttt_b200_output_norm_backward(const void* op_out, const float* post_norm_weight, const int* undo_interleave_index,
+                                  const void* d_out, void* d_op_out, float* d_post_norm_weight, float* d_post_norm_bias, int B,
+                                  int L, int H, float eps, void* stream);
 
 /* Learned residual gate (+ optional sequence reversal) of the bidirectional TTT pass.
  * Replaces SeqModelingBlock._gate / SSMGating / _reverse_text_chunks / torch.flip in

@@ -240,12 +240,16 @@ def gen_layer():
                               latent_height=Hh, latent_width=Ww, t_emb=torch.zeros(1, 8))
         B, L = 2, TL + frames * tpf
         assert L % CS == 0
-        X = torch.randn(B, L, E, dtype=torch.float64)
+        X = torch.randn(B, L, E, dtype=torch.float64, requires_grad=True)
         fc = precompute_freqs_cis_3d(E // NH, Hh, Ww, frames)
-        with torch.no_grad():
-            ref = m(X, fc, md)
+        ref = m(X, fc, md)
+        gout = torch.randn(B, L, E, dtype=torch.float64)
+        ref.backward(gout)  # autograd through the reference's eager layer
+        grads = {n: p_.grad.detach().float() for n, p_ in m.named_parameters()}
+        grads["X"] = X.grad.detach().float()
         out.append(dict(kind=kind, cfg=dict(E=E, NH=NH, Hh=Hh, Ww=Ww, frames=frames, TL=TL, CS=CS, B=B, L=L, base_lr=lr, group=2),
-                        X=X.float(), P={k: v.detach().float() for k, v in m.state_dict().items()}, ref=ref.float()))
+                        X=X.detach().float(), P={k: v.detach().float() for k, v in m.state_dict().items()},
+                        ref=ref.detach().float(), gout=gout.float(), grads=grads))
     print("layer ok")
     torch.save(out, os.path.join(GOLD, "ttt_layer_ref.pt"))
 

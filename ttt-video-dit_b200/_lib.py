@@ -26,6 +26,7 @@ _SIGS = {
     "ttt_b200_process_input_backward": ([_vp] * 3 + [_fp] * 4 + [_vp] + [_vp] * 3 + [_fp] + [_vp] * 3 + [_fp] * 3 + [_i] * 5
                                         + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_output_norm": ([_vp, _fp, _fp, _vp, _vp] + [_i] * 3 + [ctypes.c_float, _vp], ctypes.c_int),
+    "ttt_b200_output_norm_backward": ([_vp, _fp, _vp, _vp, _vp, _fp, _fp] + [_i] * 3 + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_gate_forward": ([_vp, _vp, _fp, _fp, _vp, _vp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_gate_backward": ([_vp, _vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_debug_set_timing_buffer": ([_vp], ctypes.c_int),

@@ -201,6 +201,17 @@ int ttt_b200_output_norm(const void* op_out, const float* post_norm_weight, cons
                   "ttt_b200_output_norm");
 }
 
+int ttt_b200_output_norm_backward(const void* op_out, const float* post_norm_weight, const int* undo_interleave_index,
+                                  const void* d_out, void* d_op_out, float* d_post_norm_weight, float* d_post_norm_bias, int B,
+                                  int L, int H, float eps, void* stream) {
+  if (!op_out || !post_norm_weight || !d_out || !d_op_out || !d_post_norm_weight || !d_post_norm_bias)
+    return fail(-1, "ttt_b200_output_norm_backward: null pointer argument");
+  if (int rc = bind_device(op_out)) return rc;
+  return cuda_ret(tb::launch_output_norm_backward(op_out, post_norm_weight, undo_interleave_index, d_out, d_op_out,
+                                                  d_post_norm_weight, d_post_norm_bias, B, L, H, eps, (cudaStream_t)stream),
+                  "ttt_b200_output_norm_backward");
+}
+
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");

@@ -116,3 +116,8 @@ namespace tb {
 cudaError_t launch_output_norm(const void* O, const float* gamma, const float* beta, const int* index, void* out, int B, int L,
                                int H, float eps, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_output_norm_backward(const void* O, const float* gamma, const int* index, const void* gout, void* gO,
+                                        float* dgamma, float* dbeta, int B, int L, int H, float eps, cudaStream_t stream);
+}  // namespace tb

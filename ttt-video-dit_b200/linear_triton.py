@@ -71,6 +71,33 @@ def linear_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1c, b1c, dOut, checkpoint
     return dlw.sum(0), dlb.sum(0), dW1, db1, dq, dv, dk, de
 
 
+class _TTTLinearLastEta(torch.autograd.Function):
+    """TTT-Linear op on the [B,H,NC,CS] eta row (what ``process_input.prepare`` produces): no [B,H,NC,CS,CS] tensor."""
+
+    @staticmethod
+    def forward(ctx, ln_w, ln_b, W1, b1, XQ, XV, XK, last_eta, checkpoint_group_size):
+        bf = torch.bfloat16
+        out, ck, _ = linear_forward(XQ.to(bf).contiguous(), XK.to(bf).contiguous(), XV.to(bf).contiguous(), last_eta, ln_w, ln_b,
+                                    W1, b1, checkpoint_group_size)
+        ctx.save_for_backward(XQ, XV, XK, last_eta, ln_w, ln_b, *ck)
+        ctx.group = int(checkpoint_group_size)
+        return out.to(XQ.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        XQ, XV, XK, last_eta, ln_w, ln_b, W1c, b1c = ctx.saved_tensors
+        bf = torch.bfloat16
+        dlw, dlb, dW1, db1, dq, dv, dk, de = linear_backward(XQ.to(bf).contiguous(), XK.to(bf).contiguous(), XV.to(bf).contiguous(),
+                                                             last_eta, ln_w, ln_b, W1c, b1c, grad_out, ctx.group)
+        mp = XQ.dtype
+        return (dlw.reshape(ln_w.shape).to(ln_w.dtype), dlb.reshape(ln_b.shape).to(ln_b.dtype), dW1.to(W1c.dtype),
+                db1.to(b1c.dtype), dq.to(mp), dv.to(mp), dk.to(mp), de.reshape(last_eta.shape).to(last_eta.dtype), None)
+
+
+def ttt_linear_op(ln_w, ln_b, W1, b1, XQ, XV, XK, last_eta, checkpoint_group_size):
+    return _TTTLinearLastEta.apply(ln_w, ln_b, W1, b1, XQ, XV, XK, last_eta, checkpoint_group_size)
+
+
 class TritonLinear(torch.autograd.Function):
     """Same name / call signature as the reference's TritonLinear (linear_triton.py:12)."""
 

@@ -89,21 +89,44 @@ def process_input(hidden_states, P, rope_cos, rope_sin, seq_text_length, mini_ba
     return {"XQ": XQ, "XK": XK, "XV": XV, "last_eta": eta}
 
 
+class _OutputNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, op_out, post_norm_weight, post_norm_bias, eps, undo_index):
+        B, H, NC, CS, Fd = op_out.shape
+        if Fd != 64 or not (op_out.is_cuda and op_out.dtype == torch.bfloat16 and op_out.is_contiguous()):
+            raise RuntimeError("output_norm: op_out must be a contiguous CUDA bf16 tensor [B,H,NC,CS,64]")
+        dev = op_out.device
+        L = NC * CS
+        g = post_norm_weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        bt = post_norm_bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        idx = None if undo_index is None else undo_index.to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty(B, L, H * 64, device=dev, dtype=torch.bfloat16)
+        p = _lib.ptr
+        code = _lib.lib().ttt_b200_output_norm(p(op_out), p(g), p(bt), p(idx), p(out), B, L, H, float(eps), _lib.current_stream())
+        _lib.check(code, "ttt_b200_output_norm")
+        ctx.save_for_backward(op_out, g, *(() if idx is None else (idx,)))
+        ctx.cfg = (float(eps), idx is not None, post_norm_weight.dtype, post_norm_bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        op_out, g, *rest = ctx.saved_tensors
+        eps, has_idx, w_dt, b_dt = ctx.cfg
+        idx = rest[0] if has_idx else None
+        B, H, NC, CS, _ = op_out.shape
+        gout = gout.to(torch.bfloat16).contiguous()
+        gop = torch.empty_like(op_out)
+        dg = torch.empty(H * 64, device=op_out.device, dtype=torch.float32)
+        db = torch.empty(H * 64, device=op_out.device, dtype=torch.float32)
+        p = _lib.ptr
+        code = _lib.lib().ttt_b200_output_norm_backward(p(op_out), p(g), p(idx), p(gout), p(gop), p(dg), p(db), B, NC * CS, H, eps,
+                                                        _lib.current_stream())
+        _lib.check(code, "ttt_b200_output_norm_backward")
+        return gop, dg.to(w_dt), db.to(b_dt), None, None
+
+
 def output_norm(op_out, post_norm_weight, post_norm_bias, eps=1e-6, undo_index=None):
     """Output side before wo (ttt_layer.py:456,472,324,329-331): op_out bf16 [B,H,NC,CS,64] -> post_norm(transpose) in the
     caller's token order, bf16 [B,L,H*64].  undo_index: int32 [L] gather index of undo_interleave (None for one scene).
-    Forward only (sampling path)."""
-    B, H, NC, CS, Fd = op_out.shape
-    if Fd != 64 or not (op_out.is_cuda and op_out.dtype == torch.bfloat16 and op_out.is_contiguous()):
-        raise RuntimeError("output_norm: op_out must be a contiguous CUDA bf16 tensor [B,H,NC,CS,64]")
-    dev = op_out.device
-    L = NC * CS
-    g = post_norm_weight.detach().to(device=dev, dtype=torch.float32).contiguous()
-    bt = post_norm_bias.detach().to(device=dev, dtype=torch.float32).contiguous()
-    idx = None if undo_index is None else undo_index.to(device=dev, dtype=torch.int32).contiguous()
-    out = torch.empty(B, L, H * 64, device=dev, dtype=torch.bfloat16)
-    p = _lib.ptr
-    code = _lib.lib().ttt_b200_output_norm(p(op_out), p(g), p(bt), p(idx), p(out), B, L, H, float(eps), _lib.current_stream())
-    _lib.check(code, "ttt_b200_output_norm")
-    return out
-
+    Differentiable w.r.t. op_out, post_norm_weight, post_norm_bias."""
+    return _OutputNorm.apply(op_out, post_norm_weight, post_norm_bias, eps, undo_index)

@@ -1,7 +1,8 @@
 """Mirror of the reference TTT layer forward on libttt_b200.so: ``TTTMLP.forward`` / ``TTTLinear.forward``
 (ttt/models/ssm/ttt_layer.py:314-334) = process_input (:252-306) -> ``ttt`` (:429-473 / :360-398) -> post_norm -> wo ->
 undo_interleave.  Everything except the q/k/v/lr/wo Linears (library GEMMs, as in the reference) runs in this repo's
-kernels: csrc/process_input.cu, the TTT-MLP / TTT-Linear scans, csrc/output_norm.cu.  No eager fallback.
+kernels: csrc/process_input.cu, the TTT-MLP / TTT-Linear scans, csrc/output_norm.cu.  Differentiable end to end for
+kind="ttt_mlp" and "ttt_linear" (every custom op has a native backward).  No eager fallback.
 
 ``P`` uses the reference module's state_dict names: wq/wk/wv/wo ``.weight``/``.bias``, ``learnable_ttt_lr_weight`` [H,1,E],
 ``learnable_ttt_lr_bias`` [H,1], ``ttt_norm_weight``/``ttt_norm_bias`` [H,64], ``post_norm.weight``/``.bias`` [E],
@@ -33,10 +34,8 @@ def ttt_layer_forward(hidden_states, P, rope_cos, rope_sin, seq_text_length, min
         out = mlp_tk.ttt_mlp_op(P["ttt_norm_weight"], P["ttt_norm_bias"], _tile(P["W1"], B), _tile(P["b1"], B), _tile(P["W2"], B),
                                 _tile(P["b2"], B), inp["XQ"], inp["XV"], inp["XK"], inp["last_eta"], G)
     elif kind == "ttt_linear":
-        if torch.is_grad_enabled() and hidden_states.requires_grad:
-            raise RuntimeError("ttt_layer_forward(kind='ttt_linear') is the sampling path; train through TritonLinear.apply")
-        out, _, _ = linear_triton.linear_forward(inp["XQ"], inp["XK"], inp["XV"], inp["last_eta"], P["ttt_norm_weight"],
-                                                 P["ttt_norm_bias"], _tile(P["W1"], B), _tile(P["b1"], B), G)
+        out = linear_triton.ttt_linear_op(P["ttt_norm_weight"], P["ttt_norm_bias"], _tile(P["W1"], B), _tile(P["b1"], B),
+                                          inp["XQ"], inp["XV"], inp["XK"], inp["last_eta"], G)
     else:
         raise ValueError(kind)
     x = process_input.output_norm(out.contiguous(), P["post_norm.weight"], P["post_norm.bias"], post_norm_eps, undo_interleave_index)
