@@ -13,7 +13,7 @@ import torch.nn.functional as F
 import __graft_entry__
 
 __graft_entry__.build()
-from ttt_video_dit_b200 import attention, linear_triton, process_input, seq_block
+from ttt_video_dit_b200 import attention, linear_triton, process_input, seq_block, ttt_layer
 
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 dev = "cuda"
@@ -120,8 +120,49 @@ def bench_output_norm(L=18048, H=48, B=1):
                       "frac_of_hbm_peak": bytes_ / ms / 1e6 / peaks["hbm_gbs"]}))
 
 
+def bench_block(frames=13, H=48, B=1, TL=498):
+    """SeqModelingBlock level (dit.py:163-266) at CogVideoX-5B dims, 3-second video: local attention over the one segment
+    + bidirectional gated TTT-MLP layer (forward and reversed direction), forward + backward, random bf16 weights.
+    Everything between the library Linears runs in this repo's kernels."""
+    E, tpf, CS = H * 64, 1350, 64
+    L = TL + frames * tpf
+    g = torch.Generator().manual_seed(0)
+    rb = lambda *s_: (0.02 * torch.randn(*s_, generator=g)).to(torch.bfloat16).to(dev).requires_grad_(True)
+    rf = lambda *s_: (0.02 * torch.randn(*s_, generator=g)).to(dev).requires_grad_(True)
+    P = {}
+    for n in ("wq", "wk", "wv", "wo"):
+        P[n + ".weight"], P[n + ".bias"] = rb(E, E), rb(E)
+    P["learnable_ttt_lr_weight"], P["learnable_ttt_lr_bias"] = rb(H, 1, E), rb(H, 1)
+    P["ttt_norm_weight"] = torch.ones(H, 64, device=dev, requires_grad=True); P["ttt_norm_bias"] = torch.zeros(H, 64, device=dev, requires_grad=True)
+    P["post_norm.weight"] = torch.ones(E, device=dev, requires_grad=True); P["post_norm.bias"] = torch.zeros(E, device=dev, requires_grad=True)
+    P["W1"], P["b1"], P["W2"], P["b2"] = rf(H, 64, 256), torch.zeros(H, 1, 256, device=dev, requires_grad=True), rf(H, 256, 64), torch.zeros(H, 1, 64, device=dev, requires_grad=True)
+    A = {}
+    for n in ("q", "k", "v", "o"):
+        A[n + ".weight"], A[n + ".bias"] = rb(E, E), rb(E)
+    for n in ("q_norm", "k_norm"):
+        A[n + ".weight"], A[n + ".bias"] = torch.ones(64, device=dev, dtype=torch.bfloat16, requires_grad=True), torch.zeros(64, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    gates = [torch.full((E,), 0.1, device=dev, requires_grad=True) for _ in range(4)]
+    cos_t, sin_t = torch.rand(frames * tpf, 32, generator=g).to(dev), torch.rand(frames * tpf, 32, generator=g).to(dev)
+    sin_a, cos_a = torch.rand(frames * tpf, 64, generator=g).to(dev), torch.rand(frames * tpf, 64, generator=g).to(dev)
+    vid = torch.randn(B, frames * tpf, E, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+    txt = torch.randn(B, TL, E, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+    go = torch.randn(B, L, E, generator=g).to(torch.bfloat16).to(dev)
+    layer = lambda x: ttt_layer.ttt_layer_forward(x, P, cos_t, sin_t, TL, CS, 0.1, 16, kind="ttt_mlp")
+
+    def step():
+        a = attention.local_attention(vid, txt, A, H, TL, tpf, 1, frames, 0, sin_a, cos_a)
+        y = seq_block.ssm_forward(a.contiguous(), layer, TL, 1, False, *gates)
+        y.backward(go)
+
+    ms = timeit(step, iters=5, warm=2)
+    print(json.dumps({"kernel": "SeqModelingBlock fwd+bwd (local attention + bidirectional gated TTT-MLP layer), 5B dims, 3 s",
+                      "shape": [B, L, E], "ms": ms, "tokens_per_s": B * L / ms * 1e3}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input", "output_norm"]
+    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input", "output_norm", "block"]
+    if "block" in which:
+        bench_block()
     if "output_norm" in which:
         bench_output_norm()
     if "attention_bwd" in which:
