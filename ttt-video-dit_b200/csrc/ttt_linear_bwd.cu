@@ -9,8 +9,9 @@
 //
 // CS = 16 tokens is far below tcgen05's M = 128, so every token tile is stored as 4 identical copies (tile rows
 // 32c + j, c = 0..3, j = token): the token-lane GEMM outputs then show each token in all four TMEM lane quadrants and the
-// 4 warps of a group split the 64 feature columns into 16-column quarters (lanes 16-31 of every warp are idle).  LayerNorm
-// row sums are exchanged between the 4 warps through shared memory + a named barrier.  Two warp groups:
+// warps of a group split the 64 feature columns between them (16-column quarters in the K group, 32-column halves in the
+// Q group; lanes 16-31 of every warp are idle).  LayerNorm row sums are exchanged between the warps of a group through
+// shared memory + a named barrier.  Roles:
 //   K group (warps 0-3): the sequential chain   dW' -> bf16 image -> dG = K.dW' , dK = G.dW'^T -> second-order LN
 //                         backward -> dZ1 -> dK += dZ1.W1^T , dW^T += dZ1^T.K
 //   Q group (warps 4-5): everything that does not depend on the carried gradient (Z1bar recompute, output-LN backward,
