@@ -9,7 +9,7 @@ PROBES = {
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from test_gpu_umma import run_umma
-for mode, N, K in [(0,64,64),(0,128,64),(0,64,256),(3,64,64),(3,128,64),(2,64,64),(2,64,128),(1,64,64),(1,64,256),(6,64,256)]:
+for mode, N, K in [(0,64,64),(7,64,64),(7,128,64),(7,64,128),(8,64,64),(8,64,128),(6,64,256)]:
     try:
         print('umma mode', mode, 'N', N, 'K', K, 'relmax', run_umma(mode, N, K), flush=True)
     except Exception as e:

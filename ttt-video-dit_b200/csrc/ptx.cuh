@@ -158,6 +158,16 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM ("TS" form): A[128 lanes][16 k] sits in 8 consecutive 32-bit TMEM columns of the lanes (two bf16 of
+// consecutive k per column, low half = even k), always K-major; B through a shared-memory descriptor as above.
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // tcgen05.ld 32x32b: thread i of the warp reads TMEM lane (lane_base+i), N consecutive 32-bit columns.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
