@@ -232,7 +232,7 @@ import torch, sys, time
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import attention
-for (B,T,H) in [(1,128,1),(1,256,1),(2,300,3),(1,1000,2),(1,129,1)]:
+for (B,T,H) in [(1,128,1),(2,300,3),(1,1000,2),(1,129,1),(1,4096,16)]:
     g = torch.Generator().manual_seed(1000 + T)
     q, k, v, go = (torch.randn(B, T, H, 64, generator=g).to(torch.bfloat16) for _ in range(4))
     q = q * 2.0
@@ -245,6 +245,13 @@ for (B,T,H) in [(1,128,1),(1,256,1),(2,300,3),(1,1000,2),(1,129,1)]:
     tr = lambda t: t.permute(0, 2, 1, 3)
     ref = O.sdpa_math(tr(qr), tr(kr), tr(vr)).permute(0, 2, 1, 3); ref.backward(go.float())
     print((B,T,H), 'out', '%%.2e' %% O.rel_err(out.float().cpu(), ref.detach()), {n: float('%%.2e' %% O.rel_err(a.grad.float().cpu(), b.grad)) for n,a,b in (('dq',qc,qr),('dk',kc,kr),('dv',vc,vr))}, flush=True)
+    g1 = [t.grad.clone() for t in (qc,kc,vc)]
+    same = True
+    for rep in range(3):
+        for t in (qc,kc,vc): t.grad = None
+        out = attention.sdpa_bthd(qc, kc, vc); out.backward(go.cuda()); torch.cuda.synchronize()
+        same = same and all(torch.equal(a, t.grad) for a, t in zip(g1, (qc,kc,vc)))
+    print('   bitwise reproducible over 3 more runs:', same, flush=True)
 B,T,H = 1,18048,48
 q, k, v, go = (torch.randn(B, T, H, 64, device='cuda').to(torch.bfloat16) for _ in range(4))
 qc, kc, vc = (t.requires_grad_(True) for t in (q, k, v))

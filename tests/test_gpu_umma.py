@@ -23,6 +23,7 @@ def run_umma(mode, N, K, seed=0):
 
 
 @pytest.mark.parametrize("mode,N,K", [(0, 64, 64), (0, 128, 64), (0, 64, 256), (1, 64, 64), (1, 64, 256),
-                                      (2, 64, 64), (2, 64, 128), (3, 64, 64), (3, 128, 64), (6, 64, 256)])  # modes 4/5 (A=f16 with B=bf16) trap with 'illegal instruction' on sm_100a: mixed formats are not allowed
+                                      (2, 64, 64), (2, 64, 128), (3, 64, 64), (3, 128, 64), (6, 64, 256),
+                                      (7, 64, 64), (7, 128, 64), (7, 64, 128), (8, 64, 64), (8, 64, 128)])  # 7/8: A operand from TMEM  # modes 4/5 (A=f16 with B=bf16) trap with 'illegal instruction' on sm_100a: mixed formats are not allowed
 def test_umma_modes(mode, N, K):
     assert run_umma(mode, N, K) < 1e-5

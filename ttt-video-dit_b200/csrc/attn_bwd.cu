@@ -14,9 +14,10 @@
 //   mode 1: CTA owns 128 queries (Q_i, dO_i stationary), streams 64-key sub-tiles, accumulates dQ_i in TMEM
 //           (S [128 queries x 64 keys], lse2 / delta per row = per thread).
 // Both modes: X = OWN0 . STR0^T, Y = OWN1 . STR1^T (N = 64), element-wise pass on [128 x 64] by 256 threads
-// (thread = TMEM lane x 32 columns, no reductions), bf16 tile(s) [128][64] to smem, accumulate GEMMs with the streamed
-// sub-tile as the MN-major B operand.  192 / 256 TMEM columns and 80 / 98 KB smem per CTA -> TWO CTAs per SM overlap
-// each other's MMA batches and element-wise passes (the single-CTA version with 128-wide tiles ran 1.5x slower).
+// (thread = TMEM lane x 32 columns, no reductions); P / dS are written back to TMEM as packed bf16 over the X / Y columns
+// the thread has just consumed and feed the accumulate GEMMs as the A operand FROM TMEM ("TS" form; the streamed
+// sub-tile is the MN-major B operand) -- no smem round trip for P / dS.  192 / 256 TMEM columns and 65 KB smem per CTA ->
+// TWO CTAs per SM overlap each other's MMA batches and element-wise passes.
 // Tail sub-tiles are shifted back to end at T (no out-of-bounds TMA boxes, as in the forward); streamed columns they
 // share with the previous sub-tile are masked, rows shared between two stationary tiles are computed twice, equally.
 #include <cuda.h>
@@ -36,11 +37,9 @@ constexpr uint32_t SM_OWN0 = 0;                   // stationary tile 0: K_j (mod
 constexpr uint32_t SM_OWN1 = 16384;               // stationary tile 1: V_j (mode 0) / dO_i (mode 1)       16 KB
 constexpr uint32_t SM_STR0 = 32768;               // 2 x streamed sub-tile 0: Q_u (mode 0) / K_u (mode 1)  [64][64] 8 KB
 constexpr uint32_t SM_STR1 = SM_STR0 + 16384;     // 2 x streamed sub-tile 1: dO_u (mode 0) / V_u (mode 1)
-constexpr uint32_t SM_DS = SM_STR1 + 16384;       // dS^T (mode 0) / dS (mode 1) bf16 [128][64]             16 KB
-constexpr uint32_t SM_P = SM_DS + 16384;          // P^T (mode 0 only)                                      16 KB
-constexpr uint32_t SM_MISC = SM_P + 16384;        // barriers, tmem ptr ; + mode 0: lse2 / delta of the sub-tile [2][2][64]
+constexpr uint32_t SM_MISC = SM_STR1 + 16384;     // barriers, tmem ptr ; + mode 0: lse2 / delta of the sub-tile [2][2][64]
 constexpr uint32_t SM_TOTAL0 = SM_MISC + 256 + 1024;
-constexpr uint32_t SM_TOTAL1 = SM_P + 256;        // mode 1 has no P tile: its misc block sits at SM_P
+constexpr uint32_t SM_TOTAL1 = SM_MISC + 256;
 constexpr uint32_t TM_X = 0, TM_Y = 64, TM_ACC0 = 128, TM_ACC1 = 192;  // acc0: dK / dQ, acc1: dV
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -94,7 +93,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
   const int ch = warp >> 2;                // 32-column half of the 64 streamed columns
   const int nsub = (T + BS - 1) / BS;
   const int own0 = min(own * BT, T - BT);  // first token of the stationary tile
-  constexpr uint32_t MISC = (kMode == 0) ? SM_MISC : SM_P;
+  constexpr uint32_t MISC = SM_MISC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC);
   uint64_t* bar_own = bars;
   uint64_t* bar_str = bars + 1;  // [2]
@@ -195,34 +194,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
           yv[e] = pv * ((yv[e] + nd) * scale);
         }
       }
+      // P / dS -> TMEM as packed bf16 pairs, the A operand of the accumulate GEMMs ("TS" form, umma self-test mode 8): each
+      // thread overwrites the first 16 of the 32 X / Y columns it has just consumed (its own columns only, so no
+      // cross-thread hazard; the tensor pipe is in order, so the next step's X / Y GEMMs cannot overtake these reads)
+      {
+        uint32_t pk[16];
+        if (kMode == 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t off = sw128_off(row, 4 * ch + q);
-        if (kMode == 0)
-          st_shared_v4(sbase + SM_P + off, pack_bf16(xv[8 * q], xv[8 * q + 1]), pack_bf16(xv[8 * q + 2], xv[8 * q + 3]),
-                       pack_bf16(xv[8 * q + 4], xv[8 * q + 5]), pack_bf16(xv[8 * q + 6], xv[8 * q + 7]));
-        st_shared_v4(sbase + SM_DS + off, pack_bf16(yv[8 * q], yv[8 * q + 1]), pack_bf16(yv[8 * q + 2], yv[8 * q + 3]),
-                     pack_bf16(yv[8 * q + 4], yv[8 * q + 5]), pack_bf16(yv[8 * q + 6], yv[8 * q + 7]));
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(xv[2 * i], xv[2 * i + 1]);
+          tmem_st16(tmem + lane_addr + TM_X + 32 * ch, pk);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(yv[2 * i], yv[2 * i + 1]);
+        tmem_st16(tmem + lane_addr + TM_Y + 32 * ch, pk);
+        tc_wait_st();
       }
     }
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
 
     if (tid == 0) {
       tc_fence_after();
-      // accumulate: A = bf16 tile [128][64] K-major (K = the 64 streamed tokens), B = streamed sub-tile [64 tokens][64 d] MN-major
-      const uint64_t ads = make_desc_sw128(sbase + SM_DS, 16, 1024);
+      // accumulate: A = P / dS from TMEM (K = the 64 streamed tokens: k-step kb at column 32 (kb >> 1) + 8 (kb & 1)),
+      // B = streamed sub-tile [64 tokens][64 d] MN-major
       const uint64_t bs0 = make_desc_sw128(sbase + SM_STR0 + s * 8192, 1024, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k)  // dK += dS^T Q_u  /  dQ += dS K_u
-        umma_ss(tmem + TM_ACC0, desc_advance(ads, 32 * k), desc_advance(bs0, 2048 * k), IDESC_KN, (u > 0) || (k > 0));
+        umma_ts(tmem + TM_ACC0, tmem + TM_Y + 32 * (k >> 1) + 8 * (k & 1), desc_advance(bs0, 2048 * k), IDESC_KN, (u > 0) || (k > 0));
       if (kMode == 0) {
-        const uint64_t ap = make_desc_sw128(sbase + SM_P, 16, 1024);
         const uint64_t bs1 = make_desc_sw128(sbase + SM_STR1 + s * 8192, 1024, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dV += P^T dO_u
-          umma_ss(tmem + TM_ACC1, desc_advance(ap, 32 * k), desc_advance(bs1, 2048 * k), IDESC_KN, (u > 0) || (k > 0));
+          umma_ts(tmem + TM_ACC1, tmem + TM_X + 32 * (k >> 1) + 8 * (k & 1), desc_advance(bs1, 2048 * k), IDESC_KN, (u > 0) || (k > 0));
       }
       if (u + 1 < nsub) {
         mbar_wait(&bar_str[(u + 1) & 1], ((u + 1) >> 1) & 1);

@@ -9,7 +9,8 @@
 //   S[128x128] = Q.K^T            tcgen05, A = Q tile (K-major), B = K tile (K-major), fp32 in TMEM (128 columns)
 //   softmax row-wise              two threads per query row (64 key columns each; warps w and w+4 share a TMEM lane
 //                                 quadrant), row maximum exchanged through smem; exp2 with log2e-prescale
-//   O[128x64] += P.V              A = P (bf16, smem, K-major over keys), B = V tile (MN-major view of the [key][d] tile)
+//   O[128x64] += P.V              A = P (bf16, written back to TMEM over the consumed S columns: "TS" MMA form),
+//                                 B = V tile (MN-major view of the [key][d] tile)
 // O lives in TMEM and is rescaled in place when the running maximum moves.  K/V tiles are double-buffered by TMA.
 // 112 KB smem + 256 TMEM columns per CTA -> two CTAs (16 warps) per SM overlap each other's MMA and softmax phases.
 #include <cuda.h>
@@ -20,6 +21,10 @@
 
 #include "ptx.cuh"
 #include "ttt_internal.h"
+
+#ifndef ATTN_P_IN_TMEM
+#define ATTN_P_IN_TMEM 1  // 1: P stays in TMEM as the A operand of the PV MMA (TS form); 0: P through a smem tile
+#endif
 
 namespace tb {
 namespace attn {
@@ -167,12 +172,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           lsum += s[i];
         }
       }
+#if ATTN_P_IN_TMEM
+      // P chunk -> TMEM as the A operand of the PV MMA ("TS" form, pinned by umma self-test mode 8): packed bf16 pairs in
+      // the 16 columns this thread has already consumed of its own half of the S tile (TM_S + 64 ch + 16 c)
+      {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(s[2 * i], s[2 * i + 1]);
+        tmem_st16(tmem + lane_addr + TM_S + 64 * ch + 16 * c, pk);
+      }
+#else
       // P chunk -> smem (A operand, K-major over keys): block ch, 16-byte chunks 4*c .. +3 of this row
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         st_shared_v4(sbase + SM_P + ch * 16384 + sw128_off(row, 4 * c + q), pack_bf16(s[8 * q], s[8 * q + 1]),
                      pack_bf16(s[8 * q + 2], s[8 * q + 3]), pack_bf16(s[8 * q + 4], s[8 * q + 5]), pack_bf16(s[8 * q + 6], s[8 * q + 7]));
+#endif
     }
+#if ATTN_P_IN_TMEM
+    tc_wait_st();
+#endif
     l_run = fmaf(l_run, alpha, lsum);  // partial row sum over this thread's key columns (combined in the epilogue)
     // rescale the running output (this thread: 32 of the 64 columns) only when some row of this warp moved its maximum
     // (the PV MMA of tile j-1 has completed: its commit was waited below); after the first tiles the maximum rarely moves
@@ -196,8 +215,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t db = make_desc_sw128(sbase + SM_V + slot * 16384, 1024, 1024);  // MN-major: rows = keys (K), 64 d (N)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
+#if ATTN_P_IN_TMEM
+        umma_ts(tmem + TM_O, tmem + TM_S + 64 * (k >> 2) + 8 * (k & 3), desc_advance(db, 2048 * k), IDESC_O, (j > 0) || (k > 0));
+#else
         const uint64_t da = make_desc_sw128(sbase + SM_P + (k >> 2) * 16384, 16, 1024);
         umma_ss(tmem + TM_O, desc_advance(da, 32 * (k & 3)), desc_advance(db, 2048 * k), IDESC_O, (j > 0) || (k > 0));
+#endif
       }
       tc_commit(mma_bar);
     }
