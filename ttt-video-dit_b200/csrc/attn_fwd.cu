@@ -98,29 +98,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);
   float m_run = -INFINITY, l_run = 0.f;
   uint32_t mma_phase = 0;
-  mbar_wait(bar_q, 0);
+  auto issue_s = [&](int jn) {  // S = Q . K_jn^T -> TM_S (thread 0, after the K tile of jn has landed)
+    const uint64_t da = make_desc_sw128(sbase + SM_Q, 16, 1024);
+    const uint64_t db = make_desc_sw128(sbase + SM_K + (jn & 1) * 16384, 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_ss(tmem + TM_S, desc_advance(da, 32 * k), desc_advance(db, 32 * k), IDESC_S, k > 0);
+  };
+  if (tid == 0) {
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_kv[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    tc_commit(mma_bar);
+  }
 
   for (int j = 0; j < ntiles; ++j) {
     const int slot = j & 1;
-    mbar_wait(&bar_kv[slot], (j >> 1) & 1);
-    if (tid == 0) {
-      if (j + 1 < ntiles) {  // the other slot was released by the PV MMA of tile j-1 (waited below)
-        mbar_expect_tx(&bar_kv[slot ^ 1], 32768);
-        const int kb = min((j + 1) * BN, T - BN);
-        tma_load_4d(smem + SM_K + (slot ^ 1) * 16384, &tmK, 0, h, kb, b, &bar_kv[slot ^ 1]);
-        tma_load_4d(smem + SM_V + (slot ^ 1) * 16384, &tmV, 0, h, kb, b, &bar_kv[slot ^ 1]);
-      }
-      // S = Q . K_j^T
-      tc_fence_after();
-      const uint64_t da = make_desc_sw128(sbase + SM_Q, 16, 1024);
-      const uint64_t db = make_desc_sw128(sbase + SM_K + slot * 16384, 16, 1024);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tmem + TM_S, desc_advance(da, 32 * k), desc_advance(db, 32 * k), IDESC_S, k > 0);
-      tc_commit(mma_bar);
-    }
+    // one MMA batch per tile: [P.V of tile j-1, S of tile j] (issued at the end of the previous iteration)
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    if (tid == 0 && j + 1 < ntiles) {  // the other K/V slot was released by the PV MMA of tile j-1
+      mbar_expect_tx(&bar_kv[slot ^ 1], 32768);
+      const int kb = min((j + 1) * BN, T - BN);
+      tma_load_4d(smem + SM_K + (slot ^ 1) * 16384, &tmK, 0, h, kb, b, &bar_kv[slot ^ 1]);
+      tma_load_4d(smem + SM_V + (slot ^ 1) * 16384, &tmV, 0, h, kb, b, &bar_kv[slot ^ 1]);
+    }
 
     // ---- online softmax for this thread's query row
     const int kbase = min(j * BN, T - BN);
@@ -209,7 +212,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
 
-    // ---- O += P . V_j
+    // ---- O += P . V_j, then S of the next tile in the same batch (the tensor pipe is in order: the S GEMM overwrites the
+    //      S / P columns only after the PV GEMM has read P)
     if (tid == 0) {
       tc_fence_after();
       const uint64_t db = make_desc_sw128(sbase + SM_V + slot * 16384, 1024, 1024);  // MN-major: rows = keys (K), 64 d (N)
@@ -222,12 +226,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_ss(tmem + TM_O, desc_advance(da, 32 * (k & 3)), desc_advance(db, 2048 * k), IDESC_O, (j > 0) || (k > 0));
 #endif
       }
+      if (j + 1 < ntiles) {
+        mbar_wait(&bar_kv[slot ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s(j + 1);
+      }
       tc_commit(mma_bar);
     }
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
   }
+  mbar_wait(mma_bar, mma_phase);
+  tc_fence_after();
 
   // ---- epilogue: O / l -> bf16 -> out[b, q0 + row, h, 32 ch .. 32 ch + 31]
   {
