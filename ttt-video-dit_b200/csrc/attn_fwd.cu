@@ -147,7 +147,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_st1(tmem + lane_addr + TM_X + ch, __float_as_uint(mraw));
     tc_wait_st();
     tc_fence_before();
-    __syncthreads();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");  // only the two warps that share these rows
     tc_fence_after();
     {
       const uint32_t other = tmem_ld1(tmem + lane_addr + TM_X + (ch ^ 1));
