@@ -275,7 +275,8 @@ cudaError_t launch_attention_backward(const void* Q, const void* K, const void* 
       make_bthd_tmap(&do128, dOut, B, T, H, 128) || make_bthd_tmap(&q64, Q, B, T, H, 64) || make_bthd_tmap(&k64, K, B, T, H, 64) ||
       make_bthd_tmap(&v64, V, B, T, H, 64) || make_bthd_tmap(&do64, dOut, B, T, H, 64))
     return cudaErrorInvalidValue;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(attnb::attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, attnb::SM_TOTAL0), "smem attr");
     TB_TRY(cudaFuncSetAttribute(attnb::attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attnb::SM_TOTAL1), "smem attr");

@@ -296,7 +296,8 @@ cudaError_t launch_attention_forward(const void* Q, const void* K, const void* V
   CUtensorMap tq, tk, tv;
   if (make_bthd_tmap(&tq, Q, B, T, H, 128) || make_bthd_tmap(&tk, K, B, T, H, 128) || make_bthd_tmap(&tv, V, B, T, H, 128))
     return cudaErrorInvalidValue;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(attn::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SM_TOTAL), "smem attr");
     attr_done = true;

@@ -9,6 +9,13 @@ namespace tb {
 // last failing step inside a multi-launch entry point (read by capi.cu for the error message)
 extern thread_local const char* g_where;
 extern unsigned* g_timing_buf;  // device buffer [2][64] for phase timing (debug builds), may be null
+// per-device "done once" flag for launch-site initialisation: cudaFuncSetAttribute and streams / events belong to one device
+inline bool* device_once(bool (&flags)[64]) {
+  int d = 0;
+  cudaGetDevice(&d);
+  return &flags[d & 63];
+}
+
 #define TB_TRY(call, what)                 \
   do {                                     \
     cudaError_t e__ = (call);              \

@@ -668,9 +668,17 @@ cudaError_t launch_linear_backward(const void* XQ, const void* XK, const void* X
   for (int b = 0; b < nbuf; ++b) { img[b] = ws + off; off += pairs * slots * 16384; }
   for (int b = 0; b < nbuf; ++b) { b1img[b] = reinterpret_cast<float*>(ws + off); off += pairs * slots * 512; }
 
-  static bool attr_done = false;
-  static cudaStream_t sT = nullptr;
-  static cudaEvent_t evT[2], evR[2], evIn;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
+  struct Side { cudaStream_t sT; cudaEvent_t evT[2], evR[2], evIn; };
+  static Side sides[64];
+  int dev_ = 0;
+  TB_TRY(cudaGetDevice(&dev_), "cudaGetDevice");
+  Side& sd_ = sides[dev_ & 63];
+  cudaStream_t& sT = sd_.sT;
+  cudaEvent_t(&evT)[2] = sd_.evT;
+  cudaEvent_t(&evR)[2] = sd_.evR;
+  cudaEvent_t& evIn = sd_.evIn;
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(linb::ttt_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linb::SM_TOTAL), "smem attr");
     TB_TRY(cudaStreamCreateWithFlags(&sT, cudaStreamNonBlocking), "stream create");

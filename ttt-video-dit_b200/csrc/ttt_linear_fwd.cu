@@ -352,7 +352,8 @@ cudaError_t launch_linear_forward(const void* XQ, const void* XK, const void* XV
   p.Out = reinterpret_cast<__nv_bfloat16*>(Out);
   p.BH = B * H; p.H = H; p.NC = NC; p.ckpt_group = ckpt_group; p.K = (NC + ckpt_group - 1) / ckpt_group;
   p.w_stride = lin::F * lin::F; p.b_stride = lin::F;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(lin::ttt_linear_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SM_TOTAL), "smem attr");
     attr_done = true;
@@ -377,7 +378,8 @@ cudaError_t launch_linear_trajectory(const void* XK, const void* XV, const void*
   p.ln_w = ln_w; p.ln_b = ln_b; p.W1 = W1s; p.b1 = b1s; p.w_stride = w_stride; p.b_stride = b_stride;
   p.BH = B * H; p.H = H; p.NC = NC; p.ckpt_group = 1; p.K = 1;
   p.t0 = t0; p.nsteps = nsteps; p.img_slots = img_slots; p.img = img; p.b1img = b1img;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(lin::ttt_linear_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin::SM_TOTAL), "smem attr");
     attr_done = true;

@@ -692,7 +692,8 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   if (rows > 0x7FFFFFFFull) { g_where = "too many rows"; return cudaErrorInvalidValue; }
   if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows) ||
       make_token_tmap(&tdo, dOut, rows)) return cudaErrorInvalidValue;  // g_where set by make_token_tmap
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(bwd::ttt_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SM_TOTAL), "smem attr");
     attr_done = true;

@@ -262,7 +262,8 @@ cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo,
                                   const uint8_t* img, const float* b1img, const float* b2img, uint8_t* qt, float* qb1,
                                   float* qb2, void* dXQ, float* dlnw, float* dlnb, int BH, int H, int NC, int img_slots,
                                   int G, int t0, int nsteps, cudaStream_t stream) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(bwd::ttt_mlp_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::QS_TOTAL), "smem attr (q)");
     attr_done = true;

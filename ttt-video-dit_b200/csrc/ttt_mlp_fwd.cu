@@ -626,7 +626,8 @@ static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, cons
   if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
     return cudaErrorInvalidValue;
   g_where = "forward/trajectory launch";
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
     TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");

@@ -399,7 +399,8 @@ cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const 
   p.ln_w = ln_w; p.ln_b = ln_b; p.W1 = W1c; p.b1 = b1c; p.W2 = W2c; p.b2 = b2c;
   p.NC = NC; p.H = H; p.K = K; p.G = G; p.t0 = t0; p.t_end = t_end; p.img_slots = img_slots;
   p.img = img; p.b1img = b1img; p.b2img = b2img;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(traj::ttt_mlp_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, traj::SM_TOTAL), "smem attr (traj)");
     attr_done = true;
