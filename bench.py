@@ -10,7 +10,8 @@ forward scan (+ backward scan when --mode fwdbwd) for ONE layer-direction of Cog
     python bench.py --impl reference ...      # the reference's eager CPU path (oracle port) on the host cores
 
 value   = tokens/s with inputs resident in HBM (CUDA-event time, max over ranks, whole-job aggregate)
-e2e     = same through the public op with HOST (pinned) inputs: H2D of q,k,v,eta + op + D2H of the result per step
+e2e     = same through the public op with HOST (pinned) inputs: H2D of q,k,v,eta(,dOut) + op + D2H of the result per
+          step, copies double-buffered beside the kernels by ttt_video_dit_b200.host_stream.HostPipeline
 roofline= algorithmic TTT FLOPs (7U fwd, +15U bwd per head per mini-batch, U = 2*64*64*256) / kernel time vs
           MEASURED_PEAKS.json bf16 peak
 """
@@ -220,25 +221,26 @@ def main():
     kernel_ms = sum(a.elapsed_time(b) for a, b in kern_ms) / max(1, len(kern_ms))
     n_launch = launches["n"]
 
-    # ---- timed region 2: end to end from pinned host memory (H2D of this step's inputs, D2H of its result)
+    # ---- timed region 2: end to end from pinned host memory.  Every step copies its own inputs host->device and its
+    # result device->host inside the timed region; ttt_video_dit_b200.host_stream.HostPipeline (the package's host-side
+    # entry for callers that keep tokens in pinned memory) places H2D(i+1) and D2H(i-1) beside op(i) instead of in front.
+    from ttt_video_dit_b200.host_stream import HostPipeline
     host_out = torch.empty(B, H, NC, 64, 64, dtype=torch.bfloat16).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in (XQ, XK, XV, eta_last)) + (dOut.numel() * 2 if mode == "fwdbwd" else 0)
+    host_batch = (XQ, XK, XV, eta_last, dOut if mode == "fwdbwd" else None)
+    h2d = sum(t.numel() * t.element_size() for t in host_batch if t is not None)
     d2h = host_out.numel() * 2
-    for _ in range(2):
-        o = step(XQ.to(dev, non_blocking=True), XK.to(dev, non_blocking=True), XV.to(dev, non_blocking=True),
-                 eta_last.to(dev, non_blocking=True), dOut.to(dev, non_blocking=True) if mode == "fwdbwd" else None)
-        host_out.copy_(o.detach(), non_blocking=True)
+    pipe = HostPipeline(dev)
+    pipe.run((host_batch for _ in range(2)), step, host_out)
     torch.cuda.synchronize()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
     if world > 1:
         dist.barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        o = step(XQ.to(dev, non_blocking=True), XK.to(dev, non_blocking=True), XV.to(dev, non_blocking=True),
-                 eta_last.to(dev, non_blocking=True), dOut.to(dev, non_blocking=True) if mode == "fwdbwd" else None)
-        host_out.copy_(o.detach(), non_blocking=True)
+    n_e2e = pipe.run((host_batch for _ in range(args.steps)), step, host_out)
     f1.record()
     torch.cuda.synchronize()
+    assert n_e2e == args.steps and pipe.h2d_bytes == h2d * args.steps and pipe.d2h_bytes == d2h * args.steps
     ms_e2e = f0.elapsed_time(f1)
 
     t = torch.tensor([ms_total, ms_e2e, kernel_ms], device=dev)
@@ -273,7 +275,10 @@ def main():
                                f"{H} heads x 64, mini-batch 64, NC={NC} (L={L} tokens), checkpoint group {G}, one layer-direction",
                    "mode": mode, "parallelism": f"dp{world} replicas (no data-path collective)",
                    "l2": "inputs (q,k,v = %.0f MB) larger than the 126 MB L2; no explicit flush" % (3 * B * H * NC * 8192 / 1e6)},
-        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps,
+                "pipeline": "pinned host -> H2D on a copy stream (prefetch of step i+1 beside op i) -> op -> D2H on a second "
+                            "copy stream; all copies of all steps inside the timed region"},
         "gpu_launches": n_launch,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
