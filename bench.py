@@ -120,8 +120,11 @@ def cpu_threads_for_eager(heads, mode):
     best_n, best_dt = 1, None
     for n in cands:
         torch.set_num_threads(n)
-        _eager_once(O, d, mode)
-        dt = min(_eager_once(O, d, mode), _eager_once(O, d, mode))
+        _eager_once(O, d, mode)  # warm-up (thread pool start-up lands here)
+        dt = _eager_once(O, d, mode)
+        if best_dt is not None and dt > 4 * best_dt:  # far past the optimum (oversubscribed): do not spend more time here
+            break
+        dt = min(dt, _eager_once(O, d, mode))
         if best_dt is None or dt < best_dt:
             best_n, best_dt = n, dt
         elif dt > 1.5 * best_dt:

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 
 namespace tb {
@@ -14,6 +15,14 @@ inline bool* device_once(bool (&flags)[64]) {
   int d = 0;
   cudaGetDevice(&d);
   return &flags[d & 63];
+}
+// The backward orchestrators share per-device side streams and events; two host threads enqueueing on the same device are
+// serialised for the duration of the (asynchronous) enqueue.  Different devices never contend.
+inline std::mutex& device_enqueue_mutex() {
+  static std::mutex mu[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  return mu[d & 63];
 }
 
 #define TB_TRY(call, what)                 \

@@ -668,6 +668,7 @@ cudaError_t launch_linear_backward(const void* XQ, const void* XK, const void* X
   for (int b = 0; b < nbuf; ++b) { img[b] = ws + off; off += pairs * slots * 16384; }
   for (int b = 0; b < nbuf; ++b) { b1img[b] = reinterpret_cast<float*>(ws + off); off += pairs * slots * 512; }
 
+  std::lock_guard<std::mutex> enqueue_lock(device_enqueue_mutex());
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
   bool& attr_done = *device_once(attr_done_dev);
   struct Side { cudaStream_t sT; cudaEvent_t evT[2], evR[2], evIn; };

@@ -692,6 +692,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   if (rows > 0x7FFFFFFFull) { g_where = "too many rows"; return cudaErrorInvalidValue; }
   if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows) ||
       make_token_tmap(&tdo, dOut, rows)) return cudaErrorInvalidValue;  // g_where set by make_token_tmap
+  std::lock_guard<std::mutex> enqueue_lock(device_enqueue_mutex());
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
   bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
@@ -726,6 +727,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   // compact (L1.5-resident) trajectory kernel by default; TTT_B200_TRAJ=legacy runs the forward kernel in trajectory mode
   // instead (one group per launch; 48 KB loop that disturbs the K-side kernel's instruction fetch)
   static const bool legacy_traj = [] { const char* v = getenv("TTT_B200_TRAJ"); return v && v[0] == 'l'; }();
+  static const int dbg_group_env = [] { const char* v = getenv("TTT_DBG_GROUP"); return v ? atoi(v) : 0; }();
   static const int super_env = [] { const char* v = getenv("TTT_B200_SUPER"); return v ? atoi(v) : kSuper; }();
   const int m = legacy_traj ? 1 : (super_env < 1 ? 1 : (super_env > kSuper ? kSuper : super_env));
   // units in processing order (descending steps): {first group, last group}; the first unit is the last group alone
@@ -780,7 +782,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.t_hi = t1 - 1;
     p.t_lo = t0; p.t0 = t0;
     p.first = (u == 0) ? 1 : 0;
-    { const char* dg = getenv("TTT_DBG_GROUP"); p.dbg_group = dg ? atoi(dg) : 0; }
+    p.dbg_group = dbg_group_env;
     p.dbg = g_timing_buf;  // observers: the launch whose t_lo / G equals TTT_DBG_GROUP; per-launch stamps are kept
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
     TB_TRY(cudaGetLastError(), "reverse launch");
