@@ -128,6 +128,40 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
+  const uint8_t* img_bh = p.img + (size_t)bh * p.img_slots * 65536;
+  const size_t row_bh = (size_t)bh * p.NC * CS;  // token row of step 0 of this sequence
+
+  // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
+  uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
+  uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0, ph_aux = 0, ph_xb = 0;
+
+  const uint8_t* qt_bh = p.qt + (size_t)bh * p.G * 73728;
+  // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t.  Thread 0 only.
+  auto load_xb = [&](int t, uint32_t xs) {  // Xbar2^T factor tile of step t
+    mbar_expect_tx(bar_xb, 32768);
+    bulk_load_1d(smem + xs, qt_bh + (size_t)(t - p.t0) * 73728, 32768, bar_xb);
+  };
+  auto load_q_rest = [&](int t, uint32_t zs) {  // Q_t tile, dZbar1^T -> slot zs, dZbar2 -> TT0
+    const uint8_t* src = qt_bh + (size_t)(t - p.t0) * 73728;
+    mbar_expect_tx(bar_qd, 8192 + 32768 + 8192);
+    tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)t * CS), bar_qd);
+    bulk_load_1d(smem + zs, src + 32768, 32768, bar_qd);
+    bulk_load_1d(smem + SM_TT0, src + 65536, 8192, bar_qd);
+  };
+  // first iteration's loads, issued before the carried gradient is read so that both latencies overlap
+  if (tid == 0) {
+    const int t = p.t_hi;
+    const uint8_t* im = img_bh + (size_t)(t - p.t0) * 65536;
+    mbar_expect_tx(bar_w1, 32768);
+    bulk_load_1d(smem + sW1, im, 32768, bar_w1);
+    mbar_expect_tx(bar_w2, 32768);
+    bulk_load_1d(smem + SM_W2I, im + 32768, 32768, bar_w2);
+    mbar_expect_tx(bar_kv, 16384);
+    tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
+    tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
+    load_xb(t, sA);
+    load_q_rest(t, sB);
+  }
   // ---- carried state gradient -> TMEM
   float db1r = p.first ? 0.f : p.db1s[(size_t)bh * HID + j];
   {
@@ -151,40 +185,6 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     tc_wait_st();
-  }
-  const uint8_t* img_bh = p.img + (size_t)bh * p.img_slots * 65536;
-  const size_t row_bh = (size_t)bh * p.NC * CS;  // token row of step 0 of this sequence
-
-  // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
-  uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
-  uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0, ph_aux = 0, ph_xb = 0;
-
-  const uint8_t* qt_bh = p.qt + (size_t)bh * p.G * 73728;
-  // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t.  Thread 0 only.
-  auto load_xb = [&](int t, uint32_t xs) {  // Xbar2^T factor tile of step t
-    mbar_expect_tx(bar_xb, 32768);
-    bulk_load_1d(smem + xs, qt_bh + (size_t)(t - p.t0) * 73728, 32768, bar_xb);
-  };
-  auto load_q_rest = [&](int t, uint32_t zs) {  // Q_t tile, dZbar1^T -> slot zs, dZbar2 -> TT0
-    const uint8_t* src = qt_bh + (size_t)(t - p.t0) * 73728;
-    mbar_expect_tx(bar_qd, 8192 + 32768 + 8192);
-    tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)t * CS), bar_qd);
-    bulk_load_1d(smem + zs, src + 32768, 32768, bar_qd);
-    bulk_load_1d(smem + SM_TT0, src + 65536, 8192, bar_qd);
-  };
-  // first iteration's loads
-  if (tid == 0) {
-    const int t = p.t_hi;
-    const uint8_t* im = img_bh + (size_t)(t - p.t0) * 65536;
-    mbar_expect_tx(bar_w1, 32768);
-    bulk_load_1d(smem + sW1, im, 32768, bar_w1);
-    mbar_expect_tx(bar_w2, 32768);
-    bulk_load_1d(smem + SM_W2I, im + 32768, 32768, bar_w2);
-    mbar_expect_tx(bar_kv, 16384);
-    tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
-    tma_load_2d(smem + SM_TV, &tmV, 0, (int)(row_bh + (size_t)t * CS), bar_kv);
-    load_xb(t, sA);
-    load_q_rest(t, sB);
   }
   fence_proxy_async();
   tc_fence_before();

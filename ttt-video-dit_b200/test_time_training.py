@@ -76,12 +76,16 @@ _ws_cache = {}
 
 
 def _workspace(B, H, G, device):
+    """Recompute workspace, cached per (device, stream): calls on one stream are ordered, so they can share it; a call on
+    another stream gets its own (the torch allocator only orders reuse within the allocating stream)."""
     n = _lib.lib().ttt_b200_mlp_backward_workspace_bytes(B, H, G)
-    key = (device, n)
-    if key not in _ws_cache:
-        _ws_cache.clear()
-        _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=device)
-    return _ws_cache[key], n
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() != n:
+        if len(_ws_cache) >= 4:
+            _ws_cache.clear()
+        ws = _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=device)
+    return ws, n
 
 
 def ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkpoints, b1_checkpoints,
