@@ -39,6 +39,12 @@ def _worker(rank, world, port, NC, H, direction, ret):
         out, _, last = O.ttt_mlp_primal_forward(q_, k_, v_, l_, lw, lb, *st, 1 << 30)
         return out, last
     scan_fn.next_h = 0
+    if os.environ.get("TTT_TEST_TAKES_HEADS") == "1":  # the protocol cuda_scan_fn uses: heads=slice from sharded_scan
+        def scan_fn(q_, k_, v_, l_, st, heads=None):
+            assert heads is not None and heads.stop - heads.start == q_.shape[1]
+            out, _, last = O.ttt_mlp_primal_forward(q_, k_, v_, l_, d["ln_w"][heads], d["ln_b"][heads], *st, 1 << 30)
+            return out, last
+        scan_fn.takes_heads = True
     init = (d["W1"], d["b1"], d["W2"], d["b2"])
     out, fin = seq_shard.sharded_scan(scan_fn, q, k, v, l, init, rank=rank, world=world, n_groups=2, direction=direction)
     gathered = [None] * world
@@ -84,9 +90,19 @@ def test_sharded_scan_matches_single_process(world, NC, direction):
         assert O.rel_err(a, b) < 1e-5
 
 
+def test_sharded_scan_head_slice_protocol(monkeypatch):
+    """A scan_fn flagged ``takes_heads`` receives the head slice of each pipeline group (what cuda_scan_fn relies on to pick
+    its LayerNorm rows); spawned workers inherit the switch through the environment."""
+    monkeypatch.setenv("TTT_TEST_TAKES_HEADS", "1")
+    test_sharded_scan_matches_single_process(2, 6, +1)
+
+
 def test_partition():
     from ttt_video_dit_b200 import seq_shard
     p = seq_shard.partition_minibatches(5487, 8)
     assert [e - s for s, e in p] == [686] * 7 + [685] and p[0][0] == 0 and p[-1][1] == 5487
     assert seq_shard.STATE_NUMEL * 4 == 132352
     assert [g.stop - g.start for g in seq_shard.head_groups(48, 8)] == [6] * 8
+    # latency-bound regime: one group until a launch would oversubscribe the 148 SMs
+    assert seq_shard.default_head_groups(1, 48) == 1 and seq_shard.default_head_groups(3, 48) == 1
+    assert seq_shard.default_head_groups(8, 48) == 2 and seq_shard.default_head_groups(64, 48) == 20

@@ -5,12 +5,17 @@ The interleaved token sequence is cut into ``world`` contiguous ranges of mini-b
 across ranges, so the only data-path communication is the hand-off of the carried state
 {W1[64,256], b1[256], W2[256,64], b2[64]} fp32 = 132 352 B per (batch, head) at each shard boundary: a point-to-point
 chain (``torch.distributed`` send/recv: NCCL over NVLink on GPUs, gloo in the CPU tests).  Heads are independent, so
-the chain is pipelined over head groups: rank r works on group g while rank r+1 works on group g-1
-(bubble = (world-1)/(groups+world-1)).
+the chain can be pipelined over head groups: rank r works on group g while rank r+1 works on group g-1
+(bubble = (world-1)/(groups+world-1)).  That only pays when a launch is throughput-bound: the scan is one latency chain
+per (batch, head) and a B200 holds 148 of them at once, so for B*H <= 148 a group of 6 heads takes as long as all 48 and
+the default is ONE group (``default_head_groups``).  For a single sequence the sharded scan therefore takes as long as
+the un-sharded one (the recurrence is serial whichever GPU runs it): sequence sharding buys memory capacity and token
+locality with the sequence-parallel attention, throughput comes from independent sequences (batch / data parallel).
 
 ``scan_fn(q, k, v, last_eta, state) -> (out, state_out)`` is injected: the product passes the CUDA kernel
 (``cuda_scan_fn``); the CPU gloo tests pass the oracle so the partition / ordering / pipeline logic is covered without a
-GPU.
+GPU.  A scan_fn with the attribute ``takes_heads = True`` is also given ``heads=slice`` -- the heads of the current
+pipeline group -- so that it can pick its per-head parameters (``cuda_scan_fn`` does).
 """
 from typing import Callable, List, Sequence, Tuple
 
@@ -57,13 +62,23 @@ def unpack_state(buf: torch.Tensor):
     return tuple(out)
 
 
-def sharded_scan(scan_fn: Callable, q, k, v, last_eta, init_state, *, rank: int, world: int, n_groups: int = 8,
+def default_head_groups(B: int, H: int, sms: int = 148) -> int:
+    """Head groups of the hand-off pipeline.  One scan CTA per (batch, head) is a latency chain: a launch over 6 heads takes
+    as long as one over 48, so splitting the heads only pays once a single launch would oversubscribe the SMs
+    (B*H > sms).  Below that the whole range runs as one group -- the time of a range does not shrink with fewer heads,
+    and every extra group would add a full range time to the chain."""
+    return max(1, min(H, (B * H) // sms))
+
+
+def sharded_scan(scan_fn: Callable, q, k, v, last_eta, init_state, *, rank: int, world: int, n_groups: int = None,
                  direction: int = +1, group=None):
     """Run this rank's range of the scan.  q,k,v: [B,H,NC_local,CS,F]; last_eta: [B,H,NC_local,CS,1];
     init_state: (W1,b1,W2,b2) used by the first rank of the chain only.  direction=+1: state flows rank 0 -> world-1
     (forward TTT pass); -1: world-1 -> 0 (the pass over the reversed sequence, whose first tokens live on the last rank).
     Returns (out [B,H,NC_local,CS,F], final_state or None) -- final_state only on the last rank of the chain."""
     B, H = q.shape[:2]
+    if n_groups is None:
+        n_groups = default_head_groups(B, H)
     chain = list(range(world)) if direction > 0 else list(range(world - 1, -1, -1))
     pos = chain.index(rank)
     prev_rank = chain[pos - 1] if pos > 0 else None
@@ -84,7 +99,9 @@ def sharded_scan(scan_fn: Callable, q, k, v, last_eta, init_state, *, rank: int,
         else:
             recv_work[gi].wait()
             st = unpack_state(recv_bufs[gi])
-        o, st_out = scan_fn(q[:, g].contiguous(), k[:, g].contiguous(), v[:, g].contiguous(), last_eta[:, g].contiguous(), st)
+        args = (q[:, g].contiguous(), k[:, g].contiguous(), v[:, g].contiguous(), last_eta[:, g].contiguous(), st)
+        # per-head parameters (the LayerNorm weight / bias) live in the scan_fn: tell it which heads this call covers
+        o, st_out = scan_fn(*args, heads=g) if getattr(scan_fn, "takes_heads", False) else scan_fn(*args)
         out[:, g] = o
         if next_rank is not None:
             buf = pack_state(st_out)
@@ -102,17 +119,22 @@ def sharded_scan(scan_fn: Callable, q, k, v, last_eta, init_state, *, rank: int,
 def cuda_scan_fn(ln_w, ln_b, checkpoint_group_size=1 << 30):
     """scan_fn backed by the sm_100a forward kernel (forward-only: one checkpoint group, final state exported)."""
     from . import test_time_training as tt
+    ln_w, ln_b = ln_w.reshape(-1, 64), ln_b.reshape(-1, 64)  # [H, 64] (also accepts the [1, H, 1, 64] form)
 
-    def fn(q, k, v, last_eta, st):
+    def fn(q, k, v, last_eta, st, heads=None):
         B, H, NC = q.shape[:3]
+        lw_h, lb_h = (ln_w, ln_b) if heads is None else (ln_w[heads], ln_b[heads])
+        if lw_h.shape[0] != H:
+            raise RuntimeError(f"cuda_scan_fn: {lw_h.shape[0]} LayerNorm rows for {H} heads (pass heads= or pre-sliced parameters)")
         dev = q.device
         G = min(checkpoint_group_size, NC)
         K = (NC + G - 1) // G
         out = torch.empty_like(q)
         ck = [torch.empty(B, H, K, a, b, device=dev, dtype=torch.float32) for a, b in STATE_SHAPES]
         last = [torch.empty(B, H, a, b, device=dev, dtype=torch.float32) for a, b in STATE_SHAPES]
-        lw = ln_w.reshape(1, -1, 1, 64).float().contiguous()
-        lb = ln_b.reshape(1, -1, 1, 64).float().contiguous()
+        lw = lw_h.reshape(1, -1, 1, 64).float().contiguous()
+        lb = lb_h.reshape(1, -1, 1, 64).float().contiguous()
         tt.ttt_forward(q, k, v, last_eta, lw, lb, *[s.float().contiguous() for s in st], *ck, out, G, W_last=last)
         return out, tuple(last)
+    fn.takes_heads = True
     return fn
