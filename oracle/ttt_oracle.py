@@ -2,7 +2,7 @@
 
 This file restates, in plain torch-on-CPU (fp32 or fp64), the reference's own
 PyTorch-eager TTT path.  It exists so that the CUDA kernels in
-``ttt-video-dit_b200/csrc`` can be checked on a GPU box where ``/root/reference``
+``ttt_video_dit_b200/csrc`` can be checked on a GPU box where ``/root/reference``
 does not exist.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
 

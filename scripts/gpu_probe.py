@@ -43,7 +43,7 @@ for (B,H,NC,G) in [(1,1,1,1),(1,2,4,2),(2,3,7,3),(1,4,33,16),(1,2,282,16)]:
 """ % (ROOT, ROOT),
     "timing": """
 import os
-os.environ['TTT_B200_LIB'] = os.environ.get('TTT_B200_TIMING_LIB', %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so')
+os.environ['TTT_B200_LIB'] = os.environ.get('TTT_B200_TIMING_LIB', %r + '/ttt_video_dit_b200/lib/libttt_b200_dbg.so')
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
@@ -92,7 +92,7 @@ for rep in range(2):
 """ % (ROOT, ROOT, ROOT),
     "timeline": """
 import os
-if os.environ.get('TTT_TIMELINE_DBG'): os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+if os.environ.get('TTT_TIMELINE_DBG'): os.environ['TTT_B200_LIB'] = %r + '/ttt_video_dit_b200/lib/libttt_b200_dbg.so'
 import torch, sys, json
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
@@ -168,7 +168,7 @@ for NC in (4, 6, 9):
 """ % (ROOT, ROOT),
     "lin_timing": """
 import os
-os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+os.environ['TTT_B200_LIB'] = %r + '/ttt_video_dit_b200/lib/libttt_b200_dbg.so'
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
@@ -195,7 +195,7 @@ for rep in range(2):
 """ % (ROOT, ROOT, ROOT),
     "spin": """
 import os
-os.environ['TTT_B200_LIB'] = %r + '/ttt-video-dit_b200/lib/libttt_b200_dbg.so'
+os.environ['TTT_B200_LIB'] = %r + '/ttt_video_dit_b200/lib/libttt_b200_dbg.so'
 import torch, sys
 sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O

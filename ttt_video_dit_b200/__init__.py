@@ -1,11 +1,8 @@
-"""Importable alias of the ``ttt-video-dit_b200/`` package directory (a hyphen cannot appear in a module name).
+"""B200-native (sm_100a) TTT hot path: drop-in for the reference's ttt-tk op.
 
-``import ttt_video_dit_b200`` executes ``ttt-video-dit_b200/__init__.py`` with this module's ``__path__`` pointing
-at that directory, so ``ttt_video_dit_b200.mlp_tk`` etc. resolve to the files kept there.
+Public surface mirrors the reference:
+  test_time_training.ttt_forward / ttt_backward      <-> ttt-tk/test_time_training.cpp:95-105
+  mlp_tk.TkMLP (torch.autograd.Function)             <-> ttt/models/ssm/mlp_tk.py:9
 """
-import os as _os
-
-_PKG_DIR = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "ttt-video-dit_b200")
-__path__ = [_PKG_DIR]
-with open(_os.path.join(_PKG_DIR, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_PKG_DIR, "__init__.py"), "exec"))
+__all__ = ["_lib", "test_time_training", "mlp_tk", "linear_triton", "seq_block", "seq_shard", "attention", "process_input",
+           "ttt_layer", "interleave", "host_stream"]

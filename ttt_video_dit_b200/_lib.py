@@ -44,7 +44,7 @@ def lib():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise TTTB200Error(
-                f"{LIB_PATH} not found: build it with `python ttt-video-dit_b200/build.py` "
+                f"{LIB_PATH} not found: build it with `python ttt_video_dit_b200/build.py` "
                 "(there is no CPU / eager fallback for this path)")
         L = ctypes.CDLL(LIB_PATH)
         for name, (args, res) in _SIGS.items():

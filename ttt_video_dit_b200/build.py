@@ -1,6 +1,6 @@
 """Build libttt_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python ttt-video-dit_b200/build.py [--force] [--verbose]
+    python ttt_video_dit_b200/build.py [--force] [--verbose]
 """
 import os
 import subprocess
