@@ -7,6 +7,13 @@
 #include <stdint.h>
 #include "../../ttt-video-dit_b200/csrc/ptx.cuh"
 using namespace tb;
+#ifndef TB_HAS_ELECT_ONE  // the helper lives in ptx.cuh on the elect-issue branch
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+#endif
 // variant A: divergent branch on tid (what the kernels do today)
 __global__ void kA(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint64_t* bar) {
   if (threadIdx.x == 0) {

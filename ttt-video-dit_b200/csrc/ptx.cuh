@@ -155,6 +155,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG, UBLKCP) is wrapped in its own 5-instruction election loop and
 // the descriptors are re-materialised per instruction (scripts/sass_experiments/elect_issue.cu: 12 issue slots per MMA
 // instead of 1).
+#define TB_HAS_ELECT_ONE 1
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
