@@ -12,6 +12,14 @@ import torch
 
 from . import _lib
 
+try:
+    from functools import partial
+    from torch.distributed._tensor import Shard
+    from torch.distributed._tensor.experimental import local_map
+except Exception:  # pragma: no cover
+    Shard = None
+    local_map = None
+
 
 def linear_forward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, checkpoint_group_size, want_last=False):
     """Native TTT-Linear forward.  XQ/XK/XV bf16 [B,H,NC,16,64]; last_eta bf16 [B,H,NC,16(,1)]; W1 [B,H,64,64]; b1 [B,H,1,64].
@@ -106,6 +114,18 @@ class TritonLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ttt_norm_weight, ttt_norm_bias, W1_init, b1_init, XQ_batch, XV_batch, XK_batch, eta_batch,
                 checkpoint_group_size):
+        fn = TritonLinear.forward_sharded if TritonLinear.sharded_mode else TritonLinear._forward_core
+        return fn(ctx, ttt_norm_weight, ttt_norm_bias, W1_init, b1_init, XQ_batch, XV_batch, XK_batch, eta_batch,
+                  checkpoint_group_size)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        fn = TritonLinear.backward_sharded if TritonLinear.sharded_mode else TritonLinear._backward_core
+        return fn(ctx, grad_out)
+
+    @staticmethod
+    def _forward_core(ctx, ttt_norm_weight, ttt_norm_bias, W1_init, b1_init, XQ_batch, XV_batch, XK_batch, eta_batch,
+                      checkpoint_group_size):
         mp = XQ_batch.dtype
         bf = torch.bfloat16
         last_eta = eta_batch[:, :, :, -1, :]  # only the last row enters the scan (kernels/linear_forward.py:90-101)
@@ -117,7 +137,7 @@ class TritonLinear(torch.autograd.Function):
         return out.to(mp)
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def _backward_core(ctx, grad_out):
         XQ, XV, XK, last_eta, ln_w, ln_b, W1c, b1c = ctx.saved_tensors
         mp = XQ.dtype
         bf = torch.bfloat16
@@ -129,3 +149,22 @@ class TritonLinear(torch.autograd.Function):
         d_eta[:, :, :, -1, :] = de.to(mp)
         return (dlw.reshape(ln_w.shape).to(ln_w.dtype), dlb.reshape(ln_b.shape).to(ln_b.dtype), dW1.to(mp), db1.to(mp),
                 dq.to(mp), dv.to(mp), dk.to(mp), d_eta, None)
+
+    # --- head-sharded mode (reference linear_triton.py:262-362): entered through local_map with heads Shard(1) of the op
+    #     inputs and Shard(0) of the [H,F] norm parameters; the kernels run on the local head shard, no collective inside.
+    if local_map is not None:
+        @staticmethod
+        @partial(local_map, in_placements=(None, [Shard(0)], [Shard(0)], [Shard(1)], [Shard(1)], [Shard(1)], [Shard(1)],
+                                           [Shard(1)], [Shard(1)], None),
+                 out_placements=([Shard(1)],))
+        def forward_sharded(ctx, *a):
+            return TritonLinear._forward_core(ctx, *a)
+
+        @staticmethod
+        @partial(local_map, in_placements=(None, [Shard(1)]),
+                 out_placements=([Shard(0)], [Shard(0)], [Shard(1)], [Shard(1)], [Shard(1)], [Shard(1)], [Shard(1)],
+                                 [Shard(1)], None))
+        def backward_sharded(ctx, g):
+            return TritonLinear._backward_core(ctx, g)
+    else:  # pragma: no cover
+        forward_sharded, backward_sharded = _forward_core, _backward_core
