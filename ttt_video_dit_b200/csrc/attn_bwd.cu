@@ -88,6 +88,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int own = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row = 32 * (warp & 3) + lane;  // row of the stationary tile == TMEM lane
   const int ch = warp >> 2;                // 32-column half of the 64 streamed columns
@@ -101,7 +102,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
   float* colstat = reinterpret_cast<float*>(smem + MISC + 256);  // mode 0: [2 buffers][lse2 | delta][64]
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_init(bar_own, 1);
     mbar_init(&bar_str[0], 1);
     mbar_init(&bar_str[1], 1);
@@ -136,7 +137,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
     for (int k = 0; k < 4; ++k) umma_ss(tmem + TM_Y, desc_advance(a1, 32 * k), desc_advance(b1, 32 * k), IDESC_KK, k > 0);
   };
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_expect_tx(bar_own, 32768);
     tma_load_4d(smem + SM_OWN0, &tmOwn0, 0, h, own0, b, bar_own);
     tma_load_4d(smem + SM_OWN1, &tmOwn1, 0, h, own0, b, bar_own);
@@ -169,7 +170,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
     mbar_wait(mma_bar, mma_phase);  // X, Y of this step (and the accumulate GEMMs of the previous one) are done
     mma_phase ^= 1;
     tc_fence_after();
-    if (tid == 0 && u + 1 < nsub) load_stream(u + 1);  // slot (u+1)&1 was last read by step u-1's GEMMs
+    if (warp_u == 0 && (u + 1 < nsub) && elect_one()) load_stream(u + 1);  // slot (u+1)&1 was last read by step u-1's GEMMs
 
     // ---- P and dS for (row, 32 columns); only a shifted-back tail sub-tile needs the column masks
     {
@@ -213,7 +214,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmOwn0, const __grid_constan
     tc_fence_before();
     __syncthreads();
 
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       // accumulate: A = P / dS from TMEM (K = the 64 streamed tokens: k-step kb at column 32 (kb >> 1) + 8 (kb & 1)),
       // B = streamed sub-tile [64 tokens][64 d] MN-major

@@ -58,6 +58,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = uniform_warp_id();    // same value as warp, provably warp-uniform: single-thread issue blocks branch on it
   const int row = 32 * (warp & 3) + lane;  // query row of this thread == TMEM lane
   const int ch = warp >> 2;                // which 64 key columns of the S tile / which 32 columns of O
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -86,7 +87,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = *tmem_ptr;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_expect_tx(bar_q, 16384);
     tma_load_4d(smem + SM_Q, &tmQ, 0, h, q0, b, bar_q);
     mbar_expect_tx(&bar_kv[0], 32768);
@@ -104,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_ss(tmem + TM_S, desc_advance(da, 32 * k), desc_advance(db, 32 * k), IDESC_S, k > 0);
   };
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_wait(bar_q, 0);
     mbar_wait(&bar_kv[0], 0);
     tc_fence_after();
@@ -118,7 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    if (tid == 0 && j + 1 < ntiles) {  // the other K/V slot was released by the PV MMA of tile j-1
+    if (warp_u == 0 && j + 1 < ntiles && elect_one()) {  // the other K/V slot was released by the PV MMA of tile j-1
       mbar_expect_tx(&bar_kv[slot ^ 1], 32768);
       const int kb = min((j + 1) * BN, T - BN);
       tma_load_4d(smem + SM_K + (slot ^ 1) * 16384, &tmK, 0, h, kb, b, &bar_kv[slot ^ 1]);
@@ -214,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // ---- O += P . V_j, then S of the next tile in the same batch (the tensor pipe is in order: the S GEMM overwrites the
     //      S / P columns only after the PV GEMM has read P)
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t db = make_desc_sw128(sbase + SM_V + slot * 16384, 1024, 1024);  // MN-major: rows = keys (K), 64 d (N)
 #pragma unroll

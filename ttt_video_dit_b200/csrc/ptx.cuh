@@ -150,6 +150,20 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc];   kind::f16 (bf16/fp16 operands, fp32 accumulate)
+// One elected lane of a fully converged warp.  Single-thread tcgen05 / TMA issue must sit under a branch ptxas can prove
+// to be "one lane of a warp-uniform region": `if (warp_uniform == W && elect_one())`.  Under a plain `if (tid == 0)` every
+// uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG, UBLKCP) is wrapped in its own 5-instruction election loop and
+// the descriptors are re-materialised per instruction (scripts/sass_experiments/elect_issue.cu: 12 issue slots per MMA
+// instead of 1).
+#define TB_HAS_ELECT_ONE 1
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

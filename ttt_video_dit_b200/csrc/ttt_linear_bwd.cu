@@ -135,7 +135,8 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = tid >> 7;   // 0 = K group (warps 0-3); warps 4-5 = Q group, warp 6 = issue warp
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: the role dispatch and the issue warp branch on it
+  const int grp = warp_u >> 2;  // 0 = K group (warps 0-3); warps 4-5 = Q group, warp 6 = issue warp
   const int gw = warp & 3;    // warp within the group = TMEM lane quadrant = 16-column quarter
   const int j = lane & 15;    // token row
   const bool act = lane < 16;
@@ -434,7 +435,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       atomicAdd(p.dlnw + (size_t)bh * F + c0 + (lane >> 1), dgam[0]);
       atomicAdd(p.dlnb + (size_t)bh * F + c0 + (lane >> 1), dbet[0]);
     }
-  } else if (warp < 6) {
+  } else if (warp_u < 6) {
     // =============================================== Q group ========================================================
     // two warps (TMEM lane quadrants 0 and 1), each thread = one token x 32 columns: this group has slack, and seven
     // warps in total keep every SM sub-partition at two warps, i.e. the full 255-register budget for the K group
@@ -567,7 +568,7 @@ ttt_linear_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   }
 
-  else if (lane == 0) {
+  else if (elect_one()) {  // one lane of warp 6 (the branch above is warp-uniform)
     // =============================================== issue warp =====================================================
     for (int m = 0; m < 4; ++m)
       if (p.t_hi + 1 - m >= p.t_lo) load_image(p.t_hi + 1 - m);

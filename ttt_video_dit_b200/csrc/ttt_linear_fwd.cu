@@ -60,6 +60,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int NC = kTraj ? p.nsteps : p.NC;  // steps this launch runs (trajectory mode: a window of the sequence)
   const int s_row = tid >> 6;            // which of the two stacked sequences this W1^T row belongs to
   const int fo = tid & 63;               // output feature of this row
@@ -75,7 +76,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* mma_bar = bars + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_init(&tma_bar[0], 1);
     mbar_init(&tma_bar[1], 1);
     mbar_init(mma_bar, 1);
@@ -124,7 +125,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (!kTraj && it > 0) tma_load_2d(smem + SM_TOK + slot * 8192 + 4096 + s * 2048, &tmQ, 0, row0 + (it - 1) * CS, &tma_bar[slot]);
     }
   };
-  if (tid == 0) issue_loads(0, 0);
+  if (warp_u == 0 && elect_one()) issue_loads(0, 0);
 
   // ---- initial state -> TMEM accumulator + bf16 operand copy (+ checkpoint 0)
   float b1r = row_valid ? p.b1[(size_t)bh_row * p.b_stride + fo] : 0.f;
@@ -168,7 +169,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       eta_i = __bfloat162float(p.last_eta[((size_t)bh_tok * p.NC + (kTraj ? p.t0 : 0) + it) * CS + tt]);
     if (kTraj) {  // image of the state before this step (slot it; the last pass, it == nsteps, saves the final state)
       p.b1img[((size_t)blockIdx.x * p.img_slots + it) * 128 + tid] = b1r;
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         bulk_store_1d(p.img + ((size_t)blockIdx.x * p.img_slots + it) * 16384, smem + SM_W1B, 16384);
         bulk_commit();
       }
@@ -176,10 +177,10 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
 
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
-    if (tid == 0 && it < NC) issue_loads(it + 1, slot ^ 1);
+    if (warp_u == 0 && (it < NC) && elect_one()) issue_loads(it + 1, slot ^ 1);
 
     // ---- MMA-1: D1 = W1b^T . TOK^T   (M=128, N=64 token columns, K=64)
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t da = make_desc_sw128(sbase + SM_W1B, 16, 1024);
       const uint64_t db = make_desc_sw128(tok, 16, 1024);
@@ -277,7 +278,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncthreads();
 
     // ---- MMA-U: W1^T += G^T . K   (A MN-major: 32 token rows x 2 blocks of 64 f_out; B = K rows of the token tile)
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       if (kTraj) bulk_wait_read<0>();  // the image store must have read W1b before the epilogue below rewrites it
       tc_fence_after();
       const uint64_t da = make_desc_sw128(sbase + SM_GT, 4096, 1024);
@@ -328,7 +329,7 @@ ttt_linear_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncthreads();
   }
 
-  if (kTraj && tid == 0) bulk_wait<0>();
+  if (kTraj && warp_u == 0 && elect_one()) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<128>(tmem);

@@ -71,6 +71,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int bh = blockIdx.x, head = bh % p.H;
   const int half = warp >> 2;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
@@ -110,7 +111,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int cq = 2 * (warp >> 2) + ((warp >> 1) & 1);
   const int c0 = 16 * cq;
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -149,7 +150,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bulk_load_1d(smem + SM_TT0, src + 65536, 8192, bar_qd);
   };
   // first iteration's loads, issued before the carried gradient is read so that both latencies overlap
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     const int t = p.t_hi;
     const uint8_t* im = img_bh + (size_t)(t - p.t0) * 65536;
     mbar_expect_tx(bar_w1, 32768);
@@ -239,7 +240,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     if (has_k) {
       // ===== A1 MMA: R1 = W1 . K^T -> (S0,S1)
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         tc_fence_after();
         mma_hid(tmem + TM_S0, tmem + TM_S1, sbase + sW1, sbase + SM_TK, false, 64, false);
         tc_commit(mma_bar);
@@ -272,7 +273,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_xb, ph_xb); ph_xb ^= 1;
       // ===== apply the Q-side contribution of step t to the carried gradient (outer products of the factor tiles written
       //       by ttt_mlp_bwd_q_kernel):  dW2 += Xbar2^T dZbar2 ;  dW1^T += dZbar1^T Q
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         tc_fence_after();
         mma_hid(tmem + TM_DW2, tmem + TM_DW2 + 64, sbase + sA, sbase + SM_TT0, true, 64, true);
         mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TQ, true, 64, true);
@@ -296,7 +297,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       PHASE_SYNC();
       TICK(1);
       // ===== A3 MMA: R2: Z2 = X2 . W2 -> S2 ; B5: acc5 = X2 . CW2 -> S3
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         tc_fence_after();
         mma_tok(tmem + TM_S2, sbase + sC, sbase + SM_W2I, false);
         mma_tok(tmem + TM_S3, sbase + sC, sbase + sB, false);
@@ -305,7 +306,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       MMA_WAIT();
       TICK(4);
       // spill the X2 tile to L2 (needed again by the dW2 += X2^T dZ2 GEMM at the end of the K side)
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         bulk_store_1d(p.x2spill + (size_t)bh * 32768, smem + sC, 32768);
         bulk_commit();
       }
@@ -367,7 +368,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_st16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(tg));
         tc_wait_st();
       }
-      if (tid == 0) bulk_wait_read<0>();  // X2 tile has been read out of smem: slot sC may be overwritten
+      if (warp_u == 0 && elect_one()) bulk_wait_read<0>();  // X2 tile has been read out of smem: slot sC may be overwritten
       PHASE_SYNC();
       TICK(5);
 
@@ -375,7 +376,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       //       [H]: gradZ1, d gradZ1, DG1 -> sW1, G1eta -> sC, term2, d eta hidden-sums
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {
           tc_fence_after();
           mma_hid(tmem + TM_S0, tmem + TM_S0 + 32, sbase + SM_W2I, sbase + SM_TT1 + ch * 4096, false, 32, false);
           mma_hid(tmem + TM_S1, tmem + TM_S1 + 32, sbase + sA, sbase + SM_TK + ch * 4096, false, 32, false);
@@ -410,7 +411,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       TICK(7);
       }
       // ===== A7 MMA: dK acc: S0 = G1eta . CW1 ; S3 += DG1 . W2
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         tc_fence_after();
         mma_tok(tmem + TM_S0, sbase + sC, sbase + sA, false);
         mma_tok(tmem + TM_S3, sbase + sW1, sbase + SM_W2I, true);
@@ -418,7 +419,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       MMA_WAIT();
       TICK(8);
-      if (tid == 0) {  // sA (CW1) and sC (G1eta) are free: reload the W1 image and the X2 tile
+      if (warp_u == 0 && elect_one()) {  // sA (CW1) and sC (G1eta) are free: reload the W1 image and the X2 tile
         bulk_wait<0>();
         mbar_expect_tx(bar_w1r, 32768);
         bulk_load_1d(smem + sA, img_bh + slot * 65536, 32768, bar_w1r);
@@ -511,7 +512,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       //       then, not waited here: dW2 += DG1^T gradZ2 + X2^T dZ2 -- their completion (bar_aux) frees the DG1 and X2
       //       slots early so that next iteration's tiles stream in under A10/A11
       mbar_wait(bar_x2, ph_x2); ph_x2 ^= 1;
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         tc_fence_after();
         mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + SM_W2I, sbase + SM_TT0, false, 64, false);
         mma_hid(tmem + TM_S1, tmem + TM_S2, sbase + sB, sbase + SM_TT2, false, 64, true);
@@ -522,7 +523,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       MMA_WAIT();
       TICK(10);
-      if (tid == 0 && t > p.t_lo) {  // the W2 image buffer is free now: fetch the next one
+      if (warp_u == 0 && (t > p.t_lo) && elect_one()) {  // the W2 image buffer is free now: fetch the next one
         mbar_expect_tx(bar_w2, 32768);
         bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
       }
@@ -548,7 +549,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       mbar_wait(bar_w1r, ph_w1r); ph_w1r ^= 1;
       mbar_wait(bar_aux, ph_aux); ph_aux ^= 1;   // DG1 (sW1) and X2 (sC) are no longer read by any MMA
-      if (tid == 0 && t > p.t_lo) {
+      if (warp_u == 0 && (t > p.t_lo) && elect_one()) {
         mbar_expect_tx(bar_w1, 32768);
         bulk_load_1d(smem + sC, img_bh + (size_t)(t - 1 - p.t0) * 65536, 32768, bar_w1);
         load_xb(t - 1, sW1);
@@ -556,7 +557,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       PHASE_SYNC();
       TICK(11);
       // ===== A11 MMA: dK: S0 += dZ1 . W1 ; dW1^T += dZ1^T K
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one()) {
         tc_fence_after();
         mma_tok(tmem + TM_S0, sbase + sB, sbase + sA, true);
         mma_hid(tmem + TM_DW1, tmem + TM_DW1 + 64, sbase + sB, sbase + SM_TK, true, 64, true);
@@ -578,7 +579,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // next iteration's remaining loads (buffers last used by the A11 batch): K/V tiles, Q tile, dZbar1^T -> sA, dZbar2 -> TT0
     const bool more = t > p.t_lo;
-    if (tid == 0 && more) {
+    if (warp_u == 0 && (more) && elect_one()) {
       const int tn = t - 1;
       mbar_expect_tx(bar_kv, 16384);
       tma_load_2d(smem + SM_TK, &tmK, 0, (int)(row_bh + (size_t)tn * CS), bar_kv);

@@ -67,6 +67,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int sl = blockIdx.x, bh = blockIdx.y, head = bh % p.H;
   const int s = p.t0 + sl;
   const int half = warp >> 2;
@@ -88,7 +89,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* bar_qd = bars + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_init(mma_bar, 1);
     mbar_init(bar_w, 1);
     mbar_init(bar_qd, 1);
@@ -109,7 +110,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const size_t row = ((size_t)bh * p.NC + s) * 64;
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     const uint8_t* im = p.img + slot * 65536;
     mbar_expect_tx(bar_w, 65536);
     bulk_load_1d(smem + QS_W1I, im, 32768, bar_w);
@@ -123,7 +124,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   mbar_wait(bar_qd, 0);
 
   // ===== Q1 MMA: Zbar1^T = W1 . Q^T -> (S0,S1)
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     tc_fence_after();
     mma_hid_rolled(tmem + QT_S0, tmem + QT_S1, sbase + QS_W1I, sbase + QS_TQ);
     tc_commit(mma_bar);
@@ -146,7 +147,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   PHASE_SYNC();
   // ===== Q3 MMA: Zbar2 = Xbar2 . W2 -> S2 (rows duplicated on lanes 64-127)
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     tc_fence_after();
     mma_tok_rolled(tmem + QT_S2, sbase + QS_XB, sbase + QS_W2I);
     tc_commit(mma_bar);
@@ -198,7 +199,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   PHASE_SYNC();
   // ===== Q5 MMA: dXbar2^T = W2 . dZbar2^T -> (S0,S1)
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     tc_fence_after();
     mma_hid_rolled(tmem + QT_S0, tmem + QT_S1, sbase + QS_W2I, sbase + QS_TT0);
     tc_commit(mma_bar);
@@ -224,7 +225,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   PHASE_SYNC();
   // ===== Q7 MMA: dQ_u = dZbar1 . W1 -> S2 ; factor tiles -> global scratch
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     tc_fence_after();
     mma_tok_rolled(tmem + QT_S2, sbase + QS_ZB, sbase + QS_W1I);
     tc_commit(mma_bar);
@@ -250,7 +251,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int f = 0; f < 16; ++f) a[f] += d[f];
     st_global16(p.dXQ + (row + trow) * 64 + c0, a);
   }
-  if (tid == 0) bulk_wait_read<0>();  // smem of the factor tiles must stay valid until the bulk stores have read it
+  if (warp_u == 0 && elect_one()) bulk_wait_read<0>();  // smem of the factor tiles must stay valid until the bulk stores have read it
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);

@@ -143,6 +143,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int bh = blockIdx.x;
   const int head = bh % p.H;
   const int NC = kTraj ? p.nsteps : p.NC;  // number of steps this launch runs
@@ -158,7 +159,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float2* xs2 = reinterpret_cast<float2*>(smem + SM_XB + 2048);  // [2][64]   (s1, s2) of the K side
   float* db2acc = reinterpret_cast<float*>(smem + SM_XB + 3072);  // [64] column sums of G2, folded into b2 in P6
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_init(&tma_bar[0], 1);
     mbar_init(&tma_bar[1], 1);
     mbar_init(mma_bar, 1);
@@ -186,7 +187,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* img0 = kTraj ? p.img + (size_t)bh * p.img_slots * 65536 : nullptr;
 
   // prologue TMA: K_0, V_0 into slot 0
-  if (tid == 0 && NC > 0) {
+  if (warp_u == 0 && (NC > 0) && elect_one()) {
     mbar_expect_tx(&tma_bar[0], 16384);
     tma_load_2d(smem + SM_KQ, &tmK, 0, (int)row_base, &tma_bar[0]);
     tma_load_2d(smem + SM_V, &tmV, 0, (int)row_base, &tma_bar[0]);
@@ -245,7 +246,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     tc_commit(mma_bar);
   };
-  if (tid == 0 && NC > 0) issue_p1(0);
+  if (warp_u == 0 && (NC > 0) && elect_one()) issue_p1(0);
   TICK_DECL(12, 224)
   uint32_t gp[32];  // gelu'(Z1) for this thread's hidden unit, 64 tokens, packed bf16x2
 
@@ -265,7 +266,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     TICK(0);
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
     TICK(1);
-    if (tid == 0 && (kTraj ? (it + 1 < NC) : (it < NC))) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
+    if (warp_u == 0 && ((kTraj ? (it + 1 < NC) : (it < NC))) && elect_one()) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
       const int ns = slot ^ 1;
       const bool nk = (it + 1) < NC;
       mbar_expect_tx(&tma_bar[ns], (nk ? 16384 : 0) + (kTraj ? 0 : 8192));
@@ -326,7 +327,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     TICK(3);
 
     // ---------------- P3: D2 = [X2 ; X2bar] . W2b   (M=128 tokens, N=64, K=256 hidden; both operands MN-major)
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t da = make_desc_sw128(sbase + SM_X2, 32768, 1024);
       const uint64_t db = make_desc_sw128(sbase + SM_W2B, 1024, 1024);
@@ -444,7 +445,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     TICK(5);
 
     // ---------------- P5: D3[h] = W2b[h] . G2^T  (critical) ;  W2[h] += X2^T[h] . G2  (off the critical path)
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t dg_k = make_desc_sw128(sbase + SM_G2, 16, 1024);     // B K-major view  (N = token, K = F)
       const uint64_t dg_mn = make_desc_sw128(sbase + SM_G2, 1024, 1024);  // B MN-major view (K = token, N = F)
@@ -501,7 +502,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     TICK(7);
 
     // ---------------- P7: W1^T[h] += G1^T[h] . K
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t db = make_desc_sw128(kq, 1024, 1024);  // K tile, MN-major view (K = token, N = F)
 #pragma unroll
@@ -538,7 +539,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0 && (kTraj ? (it + 1 < NC) : true)) issue_p1(it + 1);
+      if (warp_u == 0 && ((kTraj ? (it + 1 < NC) : true)) && elect_one()) issue_p1(it + 1);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];

@@ -58,6 +58,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int bh = blockIdx.x, head = bh % p.H;
   const int sub = blockIdx.y;
   const int my_t0 = p.t0 + sub * p.G;
@@ -78,7 +79,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   float2* xs1 = reinterpret_cast<float2*>(smem + SM_XB);         // [2][64] (sum z, sum z^2) per column half
   float2* xs2 = reinterpret_cast<float2*>(smem + SM_XB + 1024);  // [2][64] (s1, s2)
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_init(&tma_bar[0], 1);
     mbar_init(&tma_bar[1], 1);
     mbar_init(mma_bar, 1);
@@ -104,7 +105,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   float* b1img = p.b1img + slot0 * HID;
   float* b2img = p.b2img + slot0 * F;
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_expect_tx(&tma_bar[0], 16384);
     tma_load_2d(smem + SM_K, &tmK, 0, (int)row_base, &tma_bar[0]);
     tma_load_2d(smem + SM_V, &tmV, 0, (int)row_base, &tma_bar[0]);
@@ -154,7 +155,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
     tc_commit(mma_bar);
   };
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     bulk_store_1d(img, smem + SM_W1B, 32768);  // image of the state entering step t0 (slot 0)
     bulk_store_1d(img + 32768, smem + SM_W2B, 32768);
     bulk_commit();
@@ -172,7 +173,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     if (ln_thread) eta_raw = reinterpret_cast<const unsigned short*>(p.last_eta)[row_base + (size_t)it * CS + r];
 
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
-    if (tid == 0 && it + 1 < n) {
+    if (warp_u == 0 && (it + 1 < n) && elect_one()) {
       const int ns = slot ^ 1;
       mbar_expect_tx(&tma_bar[ns], 16384);
       tma_load_2d(smem + SM_K + ns * 8192, &tmK, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
@@ -198,7 +199,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     __syncthreads();
 
     // ---- P3: D2 = X2 . W2b  (M = 128: rows 64-127 come from the SM_GP block and are ignored; N = 64; K = 256)
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t da = make_desc_sw128(sbase + SM_X2, 32768, 1024);
       const uint64_t db = make_desc_sw128(sbase + SM_W2B, 1024, 1024);
@@ -277,7 +278,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     __syncthreads();
 
     // ---- P5: D3[h] = W2b[h] . G2^T ;  W2[h] += X2^T[h] . G2
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       const uint64_t dg_k = make_desc_sw128(sbase + SM_G2, 16, 1024);
       const uint64_t dg_mn = make_desc_sw128(sbase + SM_G2, 1024, 1024);
@@ -323,7 +324,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     __syncthreads();
 
     // ---- P7: W1^T[h] += G1^T[h] . K
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       bulk_wait_read<0>();  // the previous image store has read SM_W1B / SM_W2B (rewritten in P8, after this commit)
       tc_fence_after();
       const uint64_t db = make_desc_sw128(kt, 1024, 1024);
@@ -351,7 +352,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     tc_fence_before();
     __syncthreads();
     const bool store_img = store_last || it + 1 < n;
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       if (store_img) bulk_store_1d(img + (size_t)(it + 1) * 65536, smem + SM_W1B, 32768);
       if (it + 1 < n) issue_p1(it + 1);  // runs under the W2 conversion below
     }
@@ -369,13 +370,13 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       if (store_img) bulk_store_1d(img + (size_t)(it + 1) * 65536 + 32768, smem + SM_W2B, 32768);
       bulk_commit();
     }
   }
 
-  if (tid == 0) bulk_wait<0>();
+  if (warp_u == 0 && elect_one()) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
