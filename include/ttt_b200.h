@@ -56,6 +56,21 @@ int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const 
                           void* workspace, size_t workspace_bytes,
                           int B, int H, int NC, int checkpoint_group_size, void* stream);
 
+/* Same backward with a non-zero upstream gradient of the FINAL state: dW1_last f32 [B,H,64,256], db1_last f32 [B,H,256],
+ * dW2_last f32 [B,H,256,64], db2_last f32 [B,H,64] (all four set, or all four NULL = ttt_b200_mlp_backward).  The
+ * reference has no such input (mlp_tk.py:179-182 passes zeros): it is the hand-off message of the sequence-sharded mode,
+ * where the shard that owns the NEXT mini-batch range sends its dW1/db1/dW2/db2 (gradient w.r.t. its initial state) to
+ * the shard that owns this range -- the mirror image of W*_last in ttt_b200_mlp_forward. */
+int ttt_b200_mlp_backward_seeded(const void* XQ, const void* XK, const void* XV, const void* last_eta,
+                                 const float* ln_weight, const float* ln_bias,
+                                 const float* W1_ckpt, const float* b1_ckpt, const float* W2_ckpt, const float* b2_ckpt,
+                                 const void* dOut,
+                                 const float* dW1_last, const float* db1_last, const float* dW2_last, const float* db2_last,
+                                 float* d_ln_weight, float* d_ln_bias, float* dW1, float* db1, float* dW2, float* db2,
+                                 void* d_last_eta, void* dXQ, void* dXK, void* dXV,
+                                 void* workspace, size_t workspace_bytes,
+                                 int B, int H, int NC, int checkpoint_group_size, void* stream);
+
 /* TTT-Linear forward scan (CS = 16, head_dim 64).  Replaces the Triton launch in ttt/models/ssm/linear_triton.py:96-131
  * (kernel ttt/models/ssm/kernels/linear_forward.py:5-148).  XQ/XK/XV/Out bf16 [B,H,NC,16,64]; last_eta bf16 [B,H,NC,16];
  * W1 f32 [B,H,64,64], b1 f32 [B,H,64]; checkpoints [B,H,K,64,64] / [B,H,K,64] (may be NULL); W1_last/b1_last as the
@@ -144,19 +159,6 @@ int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_tex
 int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, const float* alpha_text,
                            const float* alpha_video, void* dres, void* ds, float* d_alpha_text, float* d_alpha_video,
                            int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream);
-
-/* Debug: device buffer (>= 512 bytes) receiving per-phase cycle counts of block 0; returns 1 if this build was compiled
- * with -DTTT_PHASE_TIMING (lib/libttt_b200_dbg.so), else 0 (the buffer is then never written). */
-int ttt_b200_debug_set_timing_buffer(void* dev_buf_512_bytes);
-
-/* Debug/self-test: D[128][N] = A[128][K] . Bm[K][N] through one tcgen05 CTA (see csrc/umma_selftest.cu). */
-int ttt_b200_debug_umma(int mode, const void* A_bf16, const void* B_bf16, float* D, int N, int K, void* stream);
-
-/* Interference experiments (scripts/gpu_probe.py): `blocks` CTAs spinning for `cycles` SM cycles; mode 0 = FMA chains,
- * mode 1 = nanosleep, mode 2 / 3 = streaming stores / loads over sink[0 .. sink_floats); smem_bytes of dynamic shared
- * memory (to pin one CTA per SM). */
-int ttt_b200_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
-                        long long sink_floats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -245,9 +245,12 @@ def ttt_mlp_step_backward(XQ, XK, W1, W2, W1n, W2n, last_eta, ln_w, ln_b, s, dW1
     return dln_w, dln_b, dW1, db1, dW2, db2, dXQ, dXV, dXK, deta
 
 
-def ttt_mlp_primal_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, W2, b2, dOut):
+def ttt_mlp_primal_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, W2, b2, dOut, dW_last=None):
     """Whole-sequence analytic backward (no checkpointing: keeps every state; small cases only).
 
+    ``dW_last`` = optional upstream gradient (dW1, db1, dW2, db2) of the FINAL state (zero at the reference's op boundary,
+    mlp_tk.py:179-182; non-zero when this range is followed by another one, see ttt_mlp_primal_backward_chunked and the
+    sequence-sharded chain).
     Returns dict with dln_w, dln_b, dW1, db1, dW2, db2 (w.r.t. the *initial* state), dXQ, dXV, dXK, dlast_eta.
     """
     B, H, NC, CS, Fd = XQ.shape
@@ -257,7 +260,10 @@ def ttt_mlp_primal_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, W2, b2, dO
         st, _, s = ttt_mlp_step_primal(*states[-1], XQ[:, :, n], XK[:, :, n], XV[:, :, n], last_eta[:, :, n], ln_w, ln_b)
         states.append(st)
         saved.append(s)
-    dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1); dW2 = torch.zeros_like(W2); db2 = torch.zeros_like(b2)
+    if dW_last is None:
+        dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1); dW2 = torch.zeros_like(W2); db2 = torch.zeros_like(b2)
+    else:
+        dW1, db1, dW2, db2 = [t.to(W1.dtype).reshape(r.shape) for t, r in zip(dW_last, (W1, b1, W2, b2))]
     dXQ = torch.empty_like(XQ); dXK = torch.empty_like(XK); dXV = torch.empty_like(XV)
     deta = torch.empty_like(last_eta)
     dlw = torch.zeros(H, Fd, dtype=XQ.dtype); dlb = torch.zeros(H, Fd, dtype=XQ.dtype)
@@ -270,6 +276,29 @@ def ttt_mlp_primal_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, W2, b2, dO
         dW1, db1, dW2, db2 = r[2:6]
         dXQ[:, :, n], dXV[:, :, n], dXK[:, :, n], deta[:, :, n] = r[6:10]
     return dict(dln_w=dlw, dln_b=dlb, dW1=dW1, db1=db1, dW2=dW2, db2=db2, dXQ=dXQ, dXV=dXV, dXK=dXK, dlast_eta=deta)
+
+
+def ttt_mlp_primal_backward_chunked(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, W2, b2, dOut, group, dW_last=None):
+    """Same gradients as ttt_mlp_primal_backward with the memory of ONE checkpoint group: a forward pass keeps only the
+    state entering every ``group`` mini-batches (what the native forward checkpoints, mlp_tk.py:95-98), then the groups are
+    replayed last to first, the state gradient handed from group to group -- the reference backward kernel's structure
+    (ttt-tk/kernels/ttt_backward/ttt.cu:453-470,824).  Lets the full 48-head, 282-step case run on a host in seconds."""
+    NC = XQ.shape[2]
+    _, ck, _ = ttt_mlp_primal_forward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, W2, b2, group)
+    K = ck[0].shape[2]
+    outs = {k: torch.empty_like(t) for k, t in (("dXQ", XQ), ("dXK", XK), ("dXV", XV), ("dlast_eta", last_eta))}
+    dlw = torch.zeros_like(ln_w.reshape(XQ.shape[1], -1)); dlb = torch.zeros_like(dlw)
+    carry = dW_last
+    for k in reversed(range(K)):
+        s, e = k * group, min(NC, (k + 1) * group)
+        st = tuple(c[:, :, k] for c in ck)
+        r = ttt_mlp_primal_backward(XQ[:, :, s:e], XK[:, :, s:e], XV[:, :, s:e], last_eta[:, :, s:e], ln_w, ln_b, *st,
+                                    dOut[:, :, s:e], dW_last=carry)
+        for name in outs:
+            outs[name][:, :, s:e] = r[name]
+        dlw += r["dln_w"]; dlb += r["dln_b"]
+        carry = (r["dW1"], r["db1"], r["dW2"], r["db2"])
+    return dict(dln_w=dlw, dln_b=dlb, dW1=carry[0], db1=carry[1], dW2=carry[2], db2=carry[3], **outs)
 
 
 # --------------------------------------------------------------------------------------

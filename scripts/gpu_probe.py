@@ -49,7 +49,7 @@ sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import _lib, mlp_tk
 buf = torch.zeros(16384, dtype=torch.int32, device='cuda')
-print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
+print('timing build:', _lib.set_timing_buffer(buf))
 B,H,NC,G = 1,int(os.environ.get('TTT_TIMING_H','48')),int(os.environ.get('TTT_TIMING_NC','64')),16
 d = O.make_inputs(B,H,NC,seed=1)
 bf = lambda t: t.to(torch.bfloat16).cuda()
@@ -174,7 +174,7 @@ sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
 from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import _lib, linear_triton
 buf = torch.zeros(8192, dtype=torch.int32, device='cuda')
-print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
+print('timing build:', _lib.set_timing_buffer(buf))
 B,H,NC,G = 1,48,256,16
 d = O.make_inputs(B,H,NC,CS=16,seed=1,base_lr=1.0,linear=True)
 dev='cuda'; bf = lambda t: t.to(torch.bfloat16).to(dev)
@@ -202,7 +202,7 @@ from oracle import ttt_oracle as O
 from ttt_video_dit_b200 import _lib, mlp_tk
 buf = torch.zeros(8192, dtype=torch.int32, device='cuda')
 sink = torch.zeros(128*1024*1024, dtype=torch.float32, device='cuda')  # 512 MB > L2
-print('timing build:', _lib.lib().ttt_b200_debug_set_timing_buffer(_lib.ptr(buf)))
+print('timing build:', _lib.set_timing_buffer(buf))
 B,H,NC,G = 1,48,32,16
 d = O.make_inputs(B,H,NC,seed=1)
 bf = lambda t: t.to(torch.bfloat16).cuda()
@@ -218,7 +218,7 @@ for label, mode, blocks, threads, smem in [('code28K 100x256', 9, 100, 256, 200*
         torch.cuda.synchronize()
         buf.zero_()
         if mode >= 0:
-            rc = _lib.lib().ttt_b200_debug_spin(blocks, threads, 6000000, mode, smem, _lib.ptr(sink), sink.numel(), side.cuda_stream)
+            rc = _lib.debug_lib().ttt_b200_debug_spin(blocks, threads, 6000000, mode, smem, _lib.ptr(sink), sink.numel(), side.cuda_stream)
             assert rc == 0, rc
         out.backward(go)
         torch.cuda.synchronize()

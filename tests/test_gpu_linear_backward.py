@@ -68,3 +68,21 @@ def test_backward_golden_reference_fixture():
         g[7] = g[7][:, :, :, -1, :]
         for n, a, b in zip(NAMES, g, fx["grads"]):
             assert O.rel_err(a.float().cpu().reshape(b.shape), b) < 2e-2, n
+
+
+def test_fp32_inputs_are_accepted():
+    """The reference's TritonLinear takes fp32 or bf16 activations (linear_triton.py:79); ours computes on bf16 MMA operands
+    either way (fp32 inputs are rounded once at the boundary) and returns outputs / gradients in the caller's dtype."""
+    d = O.make_inputs(1, 2, 6, CS=16, seed=81, base_lr=1.0, linear=True)
+    dev = "cuda"
+    leaf = lambda t: t.clone().float().to(dev).requires_grad_(True)
+    prm = [leaf(d[k]) for k in ("ln_w", "ln_b", "W1", "b1")]
+    q, v, k, e = [leaf(d[n]) for n in ("XQ", "XV", "XK", "eta")]
+    out = linear_triton.TritonLinear.apply(*prm, q, v, k, e, 4)
+    assert out.dtype == torch.float32
+    out.backward(d["dOut"].float().to(dev))
+    torch.cuda.synchronize()
+    assert all(t.grad is not None and t.grad.dtype == torch.float32 for t in (q, v, k, e))
+    ref_out, rg = oracle_grads(d)
+    assert O.rel_err(out.cpu(), ref_out) < 1e-2
+    assert O.rel_err(q.grad.cpu(), rg[4]) < 1e-2 and O.rel_err(k.grad.cpu(), rg[6]) < 1e-2

@@ -15,8 +15,8 @@ def run_umma(mode, N, K, seed=0):
     Bm = torch.randn(K, N, generator=g).to(torch.bfloat16).cuda()
     D = torch.zeros(128, N, device="cuda")
     b_arg = Bm.t().contiguous() if mode == 3 else Bm
-    code = _lib.lib().ttt_b200_debug_umma(mode, _lib.ptr(A), _lib.ptr(b_arg), _lib.ptr(D), N, K, _lib.current_stream())
-    _lib.check(code, "ttt_b200_debug_umma")
+    code = _lib.debug_lib().ttt_b200_debug_umma(mode, _lib.ptr(A), _lib.ptr(b_arg), _lib.ptr(D), N, K, _lib.current_stream(A))
+    assert code == 0, (code, _lib.debug_lib().ttt_b200_debug_last_error())
     torch.cuda.synchronize()
     ref = A.float() @ Bm.float()
     return float((D - ref).abs().max() / ref.abs().max())

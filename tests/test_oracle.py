@@ -113,3 +113,29 @@ def test_output_epilogue_restatement_matches_reference_fixture():
         uidx = O.undo_interleave_index(c["L"], c["TL"], c["chunks"], c["init_offset"], c["base_offset"]) if c["chunks"] > 1 else None
         assert O.rel_err(O.ttt_output_epilogue(fx["ep_in"], fx["pn_w"], fx["pn_b"], 1e-6, uidx), fx["ep_ref"]) < 1e-5
 
+
+
+def test_seeded_and_chunked_backward_match_autograd():
+    """The analytic backward with an upstream gradient of the FINAL state (the sequence-sharded hand-off, and what lets the
+    oracle run group by group) == autograd through the primal forward with that extra loss term."""
+    import torch
+    from oracle import ttt_oracle as O
+    d = O.make_inputs(1, 2, 5, seed=9, dtype=torch.float64)
+    le = d["eta"][:, :, :, -1, :, None]
+    names = ("XQ", "XK", "XV")
+    leaves = {n: d[n].clone().requires_grad_(True) for n in names + ("ln_w", "ln_b", "W1", "b1", "W2", "b2")}
+    lel = le.clone().requires_grad_(True)
+    out, _, last = O.ttt_mlp_primal_forward(leaves["XQ"], leaves["XK"], leaves["XV"], lel, leaves["ln_w"], leaves["ln_b"],
+                                            leaves["W1"], leaves["b1"], leaves["W2"], leaves["b2"], 1 << 30)
+    g = torch.Generator().manual_seed(1)
+    up = [torch.randn(t.shape, generator=g, dtype=torch.float64) for t in last]
+    loss = (out * d["dOut"]).sum() + sum((a * b).sum() for a, b in zip(last, up))
+    loss.backward()
+    for group in (None, 2):
+        args = (d["XQ"], d["XK"], d["XV"], le, d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], d["dOut"])
+        r = (O.ttt_mlp_primal_backward(*args, dW_last=up) if group is None
+             else O.ttt_mlp_primal_backward_chunked(*args, group, dW_last=up))
+        for k, ref in (("dXQ", leaves["XQ"].grad), ("dXK", leaves["XK"].grad), ("dXV", leaves["XV"].grad), ("dlast_eta", lel.grad),
+                       ("dW1", leaves["W1"].grad), ("db1", leaves["b1"].grad), ("dW2", leaves["W2"].grad), ("db2", leaves["b2"].grad),
+                       ("dln_w", leaves["ln_w"].grad), ("dln_b", leaves["ln_b"].grad)):
+            assert O.rel_err(r[k].reshape(ref.shape), ref) < 1e-9, (group, k)

@@ -35,7 +35,7 @@ class _SDPA(torch.autograd.Function):
         out = torch.empty_like(q)
         lse = torch.empty(B, H, T, device=q.device, dtype=torch.float32)
         code = _lib.lib().ttt_b200_attention_forward_lse(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), _lib.ptr(lse),
-                                                         B, T, H, scale, _lib.current_stream())
+                                                         B, T, H, scale, _lib.current_stream(q))
         _lib.check(code, "ttt_b200_attention_forward_lse")
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.scale = scale
@@ -50,7 +50,7 @@ class _SDPA(torch.autograd.Function):
         delta = torch.empty_like(lse)
         p = _lib.ptr
         code = _lib.lib().ttt_b200_attention_backward(p(q), p(k), p(v), p(out), p(dout), p(lse), p(delta), p(dq), p(dk), p(dv),
-                                                      B, T, H, ctx.scale, _lib.current_stream())
+                                                      B, T, H, ctx.scale, _lib.current_stream(q))
         _lib.check(code, "ttt_b200_attention_backward")
         return dq, dk, dv, None
 
@@ -63,7 +63,7 @@ def sdpa_bthd(q, k, v, scale=None):
         return _SDPA.apply(q, k, v, sc)
     out = torch.empty_like(q)
     code = _lib.lib().ttt_b200_attention_forward(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), B, T, H, sc,
-                                                 _lib.current_stream())
+                                                 _lib.current_stream(q))
     _lib.check(code, "ttt_b200_attention_forward")
     return out
 

@@ -10,6 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libttt_b200.so")
+SELFTEST_LIB = os.path.join(LIBDIR, "libttt_b200_selftest.so")  # include/ttt_b200_debug.h: development probes only
+SELFTEST_SRC = ("umma_selftest.cu", "capi_debug.cu", "tmap.cu")   # tmap.cu is shared with the production library
+PROD_EXCLUDE = ("umma_selftest.cu", "capi_debug.cu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -20,10 +23,10 @@ def sources():
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(SELFTEST_LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ttt_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("ttt_b200.h", "ttt_b200_debug.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -53,8 +56,12 @@ def _build(LIB, objdir, extra, verbose):
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
         objs.append(o)
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
-    subprocess.check_call(cmd)
+    arch = ["-gencode", "arch=compute_100a,code=sm_100a"]
+    obj_of = lambda s: os.path.join(objdir, s[:-3] + ".o")
+    subprocess.check_call([NVCC, "-shared", "-o", LIB, *[o for o in objs if os.path.basename(o) not in
+                                                          [x[:-3] + ".o" for x in PROD_EXCLUDE]], *arch])
+    if not extra:  # release build: the self-test library next to it
+        subprocess.check_call([NVCC, "-shared", "-o", SELFTEST_LIB, *[obj_of(s) for s in SELFTEST_SRC], *arch])
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -1,54 +1,8 @@
 // extern "C" surface of libttt_b200.so (declared in include/ttt_b200.h).
-#include <cuda.h>
-#include <stdio.h>
-#include <string.h>
-
 #include "../../include/ttt_b200.h"
-#include "ttt_internal.h"
+#include "capi_util.h"
 
-static thread_local char g_err[512] = "";
 namespace tb { thread_local const char* g_where = ""; unsigned* g_timing_buf = nullptr; }
-
-static int fail(int code, const char* what) {
-  snprintf(g_err, sizeof(g_err), "%s", what);
-  return code;
-}
-static int cuda_ret(cudaError_t e, const char* where) {
-  if (e == cudaSuccess) return 0;
-  snprintf(g_err, sizeof(g_err), "%s [%s]: %s (%s)", where, tb::g_where, cudaGetErrorName(e), cudaGetErrorString(e));
-  return (int)e;
-}
-
-// Bind the calling host thread to the device that owns `p`.  PyTorch's autograd worker threads (and any fresh thread)
-// have no current CUDA context in this library's (statically linked) runtime instance; driver calls such as
-// cuTensorMapEncodeTiled then fail with CUDA_ERROR_INVALID_CONTEXT and launches would go to device 0.
-typedef CUresult (*PFN_ptrAttr)(void*, CUpointer_attribute, CUdeviceptr);
-static int bind_device(const void* p) {
-  static PFN_ptrAttr fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_ptrAttr>(ptr);
-  }
-  int ord = -1;
-  if (!fn || fn(&ord, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS || ord < 0) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
-      cudaGetLastError();
-      return fail(-5, "pointer argument is not a device pointer");
-    }
-    ord = a.device;
-  }
-  static thread_local int bound = -1;
-  if (bound != ord) {
-    cudaError_t e = cudaSetDevice(ord);
-    if (e != cudaSuccess) return cuda_ret(e, "cudaSetDevice");
-    bound = ord;
-  }
-  return 0;
-}
 
 extern "C" {
 
@@ -68,7 +22,7 @@ int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const v
   if (any_ck && !all_ck) return fail(-3, "ttt_b200_mlp_forward: checkpoint buffers must be all set or all NULL");
   const bool any_l = W1_last || b1_last || W2_last || b2_last, all_l = W1_last && b1_last && W2_last && b2_last;
   if (any_l && !all_l) return fail(-3, "ttt_b200_mlp_forward: final-state buffers must be all set or all NULL");
-  if (int rc = bind_device(XQ)) return rc;
+  TB_BIND_DEVICE(XQ);
   return cuda_ret(tb::launch_mlp_forward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1, b1, W2, b2, W1_ckpt, b1_ckpt,
                                          W2_ckpt, b2_ckpt, W1_last, b1_last, W2_last, b2_last, Out, B, H, NC,
                                          checkpoint_group_size, (cudaStream_t)stream),
@@ -77,25 +31,40 @@ int ttt_b200_mlp_forward(const void* XQ, const void* XK, const void* XV, const v
 
 size_t ttt_b200_mlp_backward_workspace_bytes(int B, int H, int G) { return tb::mlp_backward_workspace_bytes(B, H, G); }
 
+int ttt_b200_mlp_backward_seeded(const void* XQ, const void* XK, const void* XV, const void* last_eta,
+                                 const float* ln_weight, const float* ln_bias, const float* W1_ckpt, const float* b1_ckpt,
+                                 const float* W2_ckpt, const float* b2_ckpt, const void* dOut, const float* dW1_last,
+                                 const float* db1_last, const float* dW2_last, const float* db2_last, float* d_ln_weight,
+                                 float* d_ln_bias, float* dW1, float* db1, float* dW2, float* db2, void* d_last_eta,
+                                 void* dXQ, void* dXK, void* dXV, void* workspace, size_t workspace_bytes, int B, int H,
+                                 int NC, int checkpoint_group_size, void* stream) {
+  if (!XQ || !XK || !XV || !last_eta || !ln_weight || !ln_bias || !W1_ckpt || !b1_ckpt || !W2_ckpt || !b2_ckpt || !dOut ||
+      !d_ln_weight || !d_ln_bias || !dW1 || !db1 || !dW2 || !db2 || !d_last_eta || !dXQ || !dXK || !dXV || !workspace)
+    return fail(-1, "ttt_b200_mlp_backward: null pointer argument");
+  const bool any_u = dW1_last || db1_last || dW2_last || db2_last, all_u = dW1_last && db1_last && dW2_last && db2_last;
+  if (any_u && !all_u) return fail(-3, "ttt_b200_mlp_backward_seeded: upstream state gradients must be all set or all NULL");
+  if (B <= 0 || H <= 0 || NC <= 0 || checkpoint_group_size <= 0)
+    return fail(-2, "ttt_b200_mlp_backward: B, H, NC and checkpoint_group_size must be positive");
+  if (workspace_bytes < tb::mlp_backward_workspace_bytes(B, H, checkpoint_group_size))
+    return fail(-4, "ttt_b200_mlp_backward: workspace too small (see ttt_b200_mlp_backward_workspace_bytes)");
+  TB_BIND_DEVICE(XQ);
+  return cuda_ret(tb::launch_mlp_backward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, W2_ckpt, b2_ckpt,
+                                          dOut, d_ln_weight, d_ln_bias, dW1, db1, dW2, db2, d_last_eta, dXQ, dXK, dXV,
+                                          workspace, workspace_bytes, B, H, NC, checkpoint_group_size,
+                                          (cudaStream_t)stream, dW1_last, db1_last, dW2_last, db2_last),
+                  "ttt_b200_mlp_backward");
+}
+
 int ttt_b200_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_weight,
                           const float* ln_bias, const float* W1_ckpt, const float* b1_ckpt, const float* W2_ckpt,
                           const float* b2_ckpt, const void* dOut, float* d_ln_weight, float* d_ln_bias, float* dW1,
                           float* db1, float* dW2, float* db2, void* d_last_eta, void* dXQ, void* dXK, void* dXV,
                           void* workspace, size_t workspace_bytes, int B, int H, int NC, int checkpoint_group_size,
                           void* stream) {
-  if (!XQ || !XK || !XV || !last_eta || !ln_weight || !ln_bias || !W1_ckpt || !b1_ckpt || !W2_ckpt || !b2_ckpt || !dOut ||
-      !d_ln_weight || !d_ln_bias || !dW1 || !db1 || !dW2 || !db2 || !d_last_eta || !dXQ || !dXK || !dXV || !workspace)
-    return fail(-1, "ttt_b200_mlp_backward: null pointer argument");
-  if (B <= 0 || H <= 0 || NC <= 0 || checkpoint_group_size <= 0)
-    return fail(-2, "ttt_b200_mlp_backward: B, H, NC and checkpoint_group_size must be positive");
-  if (workspace_bytes < tb::mlp_backward_workspace_bytes(B, H, checkpoint_group_size))
-    return fail(-4, "ttt_b200_mlp_backward: workspace too small (see ttt_b200_mlp_backward_workspace_bytes)");
-  if (int rc = bind_device(XQ)) return rc;
-  return cuda_ret(tb::launch_mlp_backward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, W2_ckpt, b2_ckpt,
-                                          dOut, d_ln_weight, d_ln_bias, dW1, db1, dW2, db2, d_last_eta, dXQ, dXK, dXV,
-                                          workspace, workspace_bytes, B, H, NC, checkpoint_group_size,
-                                          (cudaStream_t)stream),
-                  "ttt_b200_mlp_backward");
+  return ttt_b200_mlp_backward_seeded(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, W2_ckpt, b2_ckpt, dOut,
+                                      nullptr, nullptr, nullptr, nullptr, d_ln_weight, d_ln_bias, dW1, db1, dW2, db2,
+                                      d_last_eta, dXQ, dXK, dXV, workspace, workspace_bytes, B, H, NC,
+                                      checkpoint_group_size, stream);
 }
 
 int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_weight,
@@ -106,7 +75,7 @@ int ttt_b200_linear_forward(const void* XQ, const void* XK, const void* XV, cons
     return fail(-1, "ttt_b200_linear_forward: null pointer argument");
   if ((W1_ckpt == nullptr) != (b1_ckpt == nullptr) || (W1_last == nullptr) != (b1_last == nullptr))
     return fail(-3, "ttt_b200_linear_forward: W1/b1 buffer pairs must both be set or both be NULL");
-  if (int rc = bind_device(XQ)) return rc;
+  TB_BIND_DEVICE(XQ);
   return cuda_ret(tb::launch_linear_forward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1, b1, W1_ckpt, b1_ckpt, W1_last,
                                             b1_last, Out, B, H, NC, checkpoint_group_size, (cudaStream_t)stream),
                   "ttt_b200_linear_forward");
@@ -129,7 +98,7 @@ int ttt_b200_linear_backward(const void* XQ, const void* XK, const void* XV, con
     return fail(-2, "ttt_b200_linear_backward: B, H, NC and checkpoint_group_size must be positive");
   if (workspace_bytes < ttt_b200_linear_backward_workspace_bytes(B, H, NC, checkpoint_group_size))
     return fail(-4, "ttt_b200_linear_backward: workspace too small (see ttt_b200_linear_backward_workspace_bytes)");
-  if (int rc = bind_device(XQ)) return rc;
+  TB_BIND_DEVICE(XQ);
   return cuda_ret(tb::launch_linear_backward(XQ, XK, XV, last_eta, ln_weight, ln_bias, W1_ckpt, b1_ckpt, dOut,
                                              d_ln_weight, d_ln_bias, dW1, db1, d_last_eta, dXQ, dXK, dXV, workspace,
                                              workspace_bytes, B, H, NC, checkpoint_group_size, (cudaStream_t)stream),
@@ -139,7 +108,7 @@ int ttt_b200_linear_backward(const void* XQ, const void* XK, const void* XV, con
 int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void* out, int B, int T, int H, float scale,
                                void* stream) {
   if (!q || !k || !v || !out) return fail(-1, "ttt_b200_attention_forward: null pointer argument");
-  if (int rc = bind_device(q)) return rc;
+  TB_BIND_DEVICE(q);
   return cuda_ret(tb::launch_attention_forward(q, k, v, out, nullptr, B, T, H, scale, (cudaStream_t)stream),
                   "ttt_b200_attention_forward");
 }
@@ -147,7 +116,7 @@ int ttt_b200_attention_forward(const void* q, const void* k, const void* v, void
 int ttt_b200_attention_forward_lse(const void* q, const void* k, const void* v, void* out, float* lse2, int B, int T, int H,
                                    float scale, void* stream) {
   if (!q || !k || !v || !out || !lse2) return fail(-1, "ttt_b200_attention_forward_lse: null pointer argument");
-  if (int rc = bind_device(q)) return rc;
+  TB_BIND_DEVICE(q);
   return cuda_ret(tb::launch_attention_forward(q, k, v, out, lse2, B, T, H, scale, (cudaStream_t)stream),
                   "ttt_b200_attention_forward_lse");
 }
@@ -157,7 +126,7 @@ int ttt_b200_attention_backward(const void* q, const void* k, const void* v, con
                                 float scale, void* stream) {
   if (!q || !k || !v || !out || !dout || !lse2 || !delta_scratch || !dq || !dk || !dv)
     return fail(-1, "ttt_b200_attention_backward: null pointer argument");
-  if (int rc = bind_device(q)) return rc;
+  TB_BIND_DEVICE(q);
   return cuda_ret(tb::launch_attention_backward(q, k, v, out, dout, lse2, delta_scratch, dq, dk, dv, B, T, H, scale,
                                                 (cudaStream_t)stream),
                   "ttt_b200_attention_backward");
@@ -169,7 +138,7 @@ int ttt_b200_process_input(const void* xq, const void* xk, const void* xv, const
                            int mini_batch_size, float ttt_base_lr, void* stream) {
   if (!xq || !xk || !xv || !lr_logit || !rope_cos || !rope_sin || !ln_weight || !ln_bias || !XQ || !XK || !XV || !last_eta)
     return fail(-1, "ttt_b200_process_input: null pointer argument");
-  if (int rc = bind_device(xq)) return rc;
+  TB_BIND_DEVICE(xq);
   return cuda_ret(tb::launch_process_input(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_weight, ln_bias, interleave_index, XQ,
                                            XK, XV, last_eta, B, L, H, seq_text_length, mini_batch_size, ttt_base_lr,
                                            (cudaStream_t)stream),
@@ -185,7 +154,7 @@ int ttt_b200_process_input_backward(const void* xq, const void* xk, const void* 
   if (!xq || !xk || !xv || !lr_logit || !rope_cos || !rope_sin || !ln_weight || !dXQ || !dXK || !dXV || !d_last_eta || !dxq ||
       !dxk || !dxv || !d_lr_logit || !d_ln_weight || !d_ln_bias)
     return fail(-1, "ttt_b200_process_input_backward: null pointer argument");
-  if (int rc = bind_device(xq)) return rc;
+  TB_BIND_DEVICE(xq);
   return cuda_ret(tb::launch_process_input_backward(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_weight, interleave_index, dXQ,
                                                     dXK, dXV, d_last_eta, dxq, dxk, dxv, d_lr_logit, d_ln_weight, d_ln_bias, B,
                                                     L, H, seq_text_length, mini_batch_size, ttt_base_lr, (cudaStream_t)stream),
@@ -195,7 +164,7 @@ int ttt_b200_process_input_backward(const void* xq, const void* xk, const void* 
 int ttt_b200_output_norm(const void* op_out, const float* post_norm_weight, const float* post_norm_bias,
                          const int* undo_interleave_index, void* out, int B, int L, int H, float eps, void* stream) {
   if (!op_out || !post_norm_weight || !post_norm_bias || !out) return fail(-1, "ttt_b200_output_norm: null pointer argument");
-  if (int rc = bind_device(op_out)) return rc;
+  TB_BIND_DEVICE(op_out);
   return cuda_ret(tb::launch_output_norm(op_out, post_norm_weight, post_norm_bias, undo_interleave_index, out, B, L, H, eps,
                                          (cudaStream_t)stream),
                   "ttt_b200_output_norm");
@@ -206,7 +175,7 @@ int ttt_b200_output_norm_backward(const void* op_out, const float* post_norm_wei
                                   int L, int H, float eps, void* stream) {
   if (!op_out || !post_norm_weight || !d_out || !d_op_out || !d_post_norm_weight || !d_post_norm_bias)
     return fail(-1, "ttt_b200_output_norm_backward: null pointer argument");
-  if (int rc = bind_device(op_out)) return rc;
+  TB_BIND_DEVICE(op_out);
   return cuda_ret(tb::launch_output_norm_backward(op_out, post_norm_weight, undo_interleave_index, d_out, d_op_out,
                                                   d_post_norm_weight, d_post_norm_bias, B, L, H, eps, (cudaStream_t)stream),
                   "ttt_b200_output_norm_backward");
@@ -215,7 +184,7 @@ int ttt_b200_output_norm_backward(const void* op_out, const float* post_norm_wei
 int ttt_b200_gate_forward(const void* res, const void* s, const float* alpha_text, const float* alpha_video, void* out,
                           void* rev, int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!res || !s || !alpha_text || !alpha_video || !out) return fail(-1, "ttt_b200_gate_forward: null pointer argument");
-  if (int rc = bind_device(res)) return rc;
+  TB_BIND_DEVICE(res);
   return cuda_ret(tb::launch_gate_forward(res, s, alpha_text, alpha_video, out, rev, B, L, E, text_len, num_chunks,
                                           perm_s, (cudaStream_t)stream),
                   "ttt_b200_gate_forward");
@@ -226,36 +195,18 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                            int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream) {
   if (!dout || !s || !alpha_text || !alpha_video || !dres || !ds || !d_alpha_text || !d_alpha_video)
     return fail(-1, "ttt_b200_gate_backward: null pointer argument");
-  if (int rc = bind_device(dout)) return rc;
+  TB_BIND_DEVICE(dout);
   return cuda_ret(tb::launch_gate_backward(dout, drev, s, alpha_text, alpha_video, dres, ds, d_alpha_text,
                                            d_alpha_video, B, L, E, text_len, num_chunks, perm_s, (cudaStream_t)stream),
                   "ttt_b200_gate_backward");
 }
 
+#ifdef TTT_PHASE_TIMING
+/* phase-timing build only (lib/libttt_b200_dbg.so): device buffer (>= 512 bytes) receiving per-phase cycle counts */
 int ttt_b200_debug_set_timing_buffer(void* dev_buf_512_bytes) {
   tb::g_timing_buf = reinterpret_cast<unsigned*>(dev_buf_512_bytes);
-#ifdef TTT_PHASE_TIMING
   return 1;
-#else
-  return 0;
+}
 #endif
-}
-
-int ttt_b200_debug_umma(int mode, const void* A, const void* Bm, float* D, int N, int K, void* stream) {
-  if (int rc = bind_device(A)) return rc;
-  return cuda_ret(tb::launch_umma_selftest(mode, A, Bm, D, N, K, (cudaStream_t)stream), "ttt_b200_debug_umma");
-}
-
-// Occupancy / interference experiments: `blocks` CTAs that spin for `cycles` SM cycles with a tiny code footprint and no
-// memory traffic.  mode 0: dependent FMA chains (ALU busy), mode 1: nanosleep (SM occupied but idle), mode 2 / 3:
-// streaming stores / loads over sink[0 .. sink_floats).  smem_bytes of dynamic shared memory pins one CTA per SM when
-// set close to the maximum.
-int ttt_b200_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
-                        long long sink_floats, void* stream) {
-  if (!sink) return fail(-1, "ttt_b200_debug_spin: null pointer argument");
-  if (int rc = bind_device(sink)) return rc;
-  return cuda_ret(tb::launch_debug_spin(blocks, threads, cycles, mode, smem_bytes, sink, sink_floats, (cudaStream_t)stream),
-                  "ttt_b200_debug_spin");
-}
 
 }  // extern "C"

@@ -64,7 +64,9 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
                                 const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
                                 const float* b2c, const void* dOut, float* dlnw, float* dlnb, float* dW1, float* db1,
                                 float* dW2, float* db2, void* dEta, void* dXQ, void* dXK, void* dXV, void* workspace,
-                                size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream);
+                                size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream,
+                                const float* dW1_last = nullptr, const float* db1_last = nullptr,
+                                const float* dW2_last = nullptr, const float* db2_last = nullptr);
 }  // namespace tb
 
 namespace tb {
@@ -104,7 +106,7 @@ cudaError_t launch_attention_backward(const void* Q, const void* K, const void* 
 namespace tb {
 cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo, const float* ln_w, const float* ln_b,
                                   const uint8_t* img, const float* b1img, const float* b2img, uint8_t* qt, float* qb1,
-                                  float* qb2, void* dXQ, float* dlnw, float* dlnb, int BH, int H, int NC, int img_slots,
+                                  float* qb2, void* dXQ, int BH, int H, int NC, int img_slots,
                                   int G, int t0, int nsteps, cudaStream_t stream);
 }  // namespace tb
 

@@ -37,7 +37,7 @@ constexpr uint32_t SM_TT1 = 204800;    // gradZ2
 constexpr uint32_t SM_TT2 = 212992;    // -eta*gradZ2
 constexpr uint32_t SM_MISC = 221184;   // small fp32 vectors, barriers (2560 B)
 constexpr uint32_t SM_XB = SM_MISC + 2560;  // token-phase exchange buffers: float4[4][64], float2[4][64], float[4][64]
-constexpr uint32_t SM_TOTAL = SM_XB + 7168;  // 230912
+constexpr uint32_t SM_TOTAL = SM_XB + 7680;  // 231424 (+512: second-row-half accumulators of d gamma / d beta)
 static_assert(SM_TOTAL <= 231424, "smem budget: 227 KB minus the 1 KB alignment slack of the dynamic window");
 
 // ---- TMEM columns
@@ -53,10 +53,10 @@ struct BwdParams {
   float *dW1s, *dW2s, *db1s, *db2s;  // carried state gradient, fp32: [BH][256][64] x2, [BH][256], [BH][64]
   uint8_t* x2spill;                  // [BH][32 KB]
   const uint8_t* qt;                 // Q-side factor tiles [BH][G] x 73728 B (ttt_mlp_bwd_q.cu)
-  const float *qb1, *qb2;            // Q-side b1/b2 contributions [BH][G][256], [BH][G][64]
+  const float *qb1, *qb2;            // Q-side contributions [BH][G][256] (d b1), [BH][G][192] = {d b2, d gamma, d beta}
   int G;
   __nv_bfloat16 *dXQ, *dXK, *dXV, *dEta;  // outputs
-  float *dlnw, *dlnb;                     // [BH][64], accumulated with atomics (pre-zeroed by the host wrapper)
+  float *dlnw, *dlnb;                     // [BH][64], accumulated launch after launch, one writer per element (pre-zeroed by the host)
   float *dW1, *db1, *dW2, *db2;           // final gradient w.r.t. the initial state (written when t_lo == 0)
   int H, NC, img_slots;
   int t_hi, t_lo, t0;  // iterations t_hi..t_lo (descending); image slot of W_t is t - t0
@@ -88,9 +88,14 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* b2t = lnb + 64;      // b2 of W_t
   float* db2c = b2t + 64;     // d b2 carried (grad w.r.t. b2 after step t; updated in place during the iteration)
   float* etas = db2c + 64;    // eta of step t
-  float* etasum = etas + 64;  // sum over hidden units of gradZ1 * E (d eta), accumulated with shared atomics
-  float* dgam = etasum + 64;  // d gamma / d beta accumulated over the whole launch
+  // Reductions over token rows / hidden lanes are laid out so that every shared-memory word has exactly ONE writer per
+  // step (no atomics): fp32 addition is not associative, and an unordered pair of adds onto a running sum would make the
+  // whole backward bit-irreproducible (d b2 feeds every earlier step).  Row halves (warp & 1) own separate accumulators.
+  float* db2h = etas + 64;    // d b2 contributions of token rows 32-63 of the current step (merged at the loop top)
+  float* dgam = db2h + 64;    // d gamma / d beta accumulated over the whole launch, token rows 0-31 (+ Q-side partials)
   float* dbet = dgam + 64;
+  float* dgam2 = reinterpret_cast<float*>(smem + SM_XB + 7168);  // ... token rows 32-63
+  float* dbet2 = dgam2 + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_MISC + 2048);
   uint64_t* mma_bar = bars;       // tcgen05.commit
   uint64_t* bar_kv = bars + 1;    // K_t, V_t tiles
@@ -105,6 +110,9 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float4* xA = reinterpret_cast<float4*>(smem + SM_XB);          // [4][64]
   float2* xB = reinterpret_cast<float2*>(smem + SM_XB + 4096);   // [4][64]
   float* epart = reinterpret_cast<float*>(smem + SM_XB + 6144);  // [4][64]
+  // xA carries float2 payloads in .x/.y; the .z/.w words hold the 8 per-warp partial sums of the d eta reduction over the
+  // hidden lanes (one word per (warp, token)), written in A5/A6 and read in A8
+  float* esum8 = reinterpret_cast<float*>(smem + SM_XB);
   // token-phase mapping: thread <-> (row trow, column quarter cq); row r is read from TMEM lane r (warps with
   // (warp&3) < 2) or from its duplicate at lane 64+r (the others) -- both inside this warp's own lane quarter.
   const int trow = 32 * (warp & 1) + lane;
@@ -121,8 +129,8 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     lnw[tid] = p.ln_w[head * 64 + tid];
     lnb[tid] = p.ln_b[head * 64 + tid];
     db2c[tid] = p.first ? 0.f : p.db2s[(size_t)bh * 64 + tid];
-    dgam[tid] = 0.f;
-    dbet[tid] = 0.f;
+    db2h[tid] = 0.f;
+    dgam[tid] = 0.f; dbet[tid] = 0.f; dgam2[tid] = 0.f; dbet2[tid] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -194,11 +202,12 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
   float nb1 = p.b1img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * HID + j], nb2 = 0.f;
-  float nq1 = p.qb1[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * HID + j], nq2 = 0.f;
+  float nq1 = p.qb1[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * HID + j], nq2 = 0.f, nqg = 0.f, nqb = 0.f;
   unsigned short neta = 0;
   if (tid < 64) {
     nb2 = p.b2img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * F + tid];
-    nq2 = p.qb2[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * F + tid];
+    const float* q2 = p.qb2 + ((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * 192;
+    nq2 = q2[tid]; nqg = q2[64 + tid]; nqb = q2[128 + tid];
     if (p.t_hi < p.NC) neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)p.t_hi * CS + tid];
   }
   TICK(14);  // prologue
@@ -211,8 +220,11 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (tid < 64) {
       b2t[tid] = nb2;
       etas[tid] = __uint_as_float((uint32_t)neta << 16);
-      etasum[tid] = 0.f;
-      db2c[tid] += nq2;  // Q-side contribution of step t to d b2 (state after step t)
+      // merge the second row half of the previous step, then the Q-side contribution of step t (state after step t)
+      db2c[tid] = (db2c[tid] + db2h[tid]) + nq2;
+      db2h[tid] = 0.f;
+      dgam[tid] += nqg;  // Q-side (output LayerNorm) part of d gamma / d beta of step t
+      dbet[tid] += nqb;
     }
     db1r += q1t;         // ... and to d b1
     if (t > p.t_lo) {  // prefetch for iteration t-1
@@ -221,7 +233,8 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       nq1 = p.qb1[((size_t)bh * p.G + ns) * HID + j];
       if (tid < 64) {
         nb2 = p.b2img[((size_t)bh * p.img_slots + ns) * F + tid];
-        nq2 = p.qb2[((size_t)bh * p.G + ns) * F + tid];
+        const float* q2 = p.qb2 + ((size_t)bh * p.G + ns) * 192;
+        nq2 = q2[tid]; nqg = q2[64 + tid]; nqb = q2[128 + tid];
         neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)(t - 1) * CS + tid];
       }
     }
@@ -342,7 +355,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           s1 += tg[f];
           s2 = fmaf(tg[f], z[f], s2);
         }
-        xA[cq * 64 + trow] = make_float4(s1, s2, 0.f, 0.f);
+        *reinterpret_cast<float2*>(&xA[cq * 64 + trow]) = make_float2(s1, s2);
         __syncthreads();
         s1 = 0.f; s2 = 0.f;
 #pragma unroll
@@ -405,7 +418,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           st_row32(sbase + sW1, j, 4 * ch, raw);
           st_row32(sbase + sC, j, 4 * ch, pre);
           warp_colsum<32>(ep, lane);
-          atomicAdd(&etasum[32 * ch + lane], ep[0]);
+          esum8[((warp >> 1) * 64 + 32 * ch + lane) * 4 + 2 + (warp & 1)] = ep[0];  // partial of this warp's 32 hidden lanes
         }
         PHASE_SYNC();
       TICK(7);
@@ -468,7 +481,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           sdxh += dxh;
           dg[f] = dxh;                                                               // keep d_xhat
         }
-        xA[cq * 64 + trow] = make_float4(sds, sdxh, 0.f, 0.f);
+        *reinterpret_cast<float2*>(&xA[cq * 64 + trow]) = make_float2(sds, sdxh);  // .z/.w hold the d eta partials
         __syncthreads();
         sds = 0.f; sdxh = 0.f;
 #pragma unroll
@@ -492,7 +505,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_wait_st();
         }
         if (cq == 0) {  // d eta of step t
-          const float e = epart[trow] + epart[64 + trow] + epart[128 + trow] + epart[192 + trow] - etasum[trow];
+          float es = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) es += esum8[((w >> 1) * 64 + trow) * 4 + 2 + (w & 1)];  // fixed order
+          const float e = epart[trow] + epart[64 + trow] + epart[128 + trow] + epart[192 + trow] - es;
           p.dEta[row_bh + (size_t)t * CS + trow] = __float2bfloat16(e);
         }
         // column sums over this warp's 32 token rows (then shared atomics across the two row halves)
@@ -501,9 +517,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         warp_colsum16(dy, lane);
         if ((lane & 1) == 0) {
           const int f = c0 + (lane >> 1);
-          atomicAdd(&db2c[f], dg[0]);
-          atomicAdd(&dgam[f], cg[0]);
-          atomicAdd(&dbet[f], dy[0]);
+          const bool hi = (warp & 1) != 0;  // token rows 32-63: the other accumulator set (one writer per word)
+          (hi ? db2h : db2c)[f] += dg[0];
+          (hi ? dgam2 : dgam)[f] += cg[0];
+          (hi ? dbet2 : dbet)[f] += dy[0];
         }
       }
       PHASE_SYNC();
@@ -618,10 +635,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
     (fin ? p.db1 : p.db1s)[(size_t)bh * HID + j] = db1r;
-    if (tid < 64) (fin ? p.db2 : p.db2s)[(size_t)bh * 64 + tid] = db2c[tid];
-    if (tid < 64) {
-      atomicAdd(&p.dlnw[(size_t)bh * 64 + tid], dgam[tid]);
-      atomicAdd(&p.dlnb[(size_t)bh * 64 + tid], dbet[tid]);
+    if (tid < 64) (fin ? p.db2 : p.db2s)[(size_t)bh * 64 + tid] = db2c[tid] + db2h[tid];
+    if (tid < 64) {  // launches of one sequence are stream-ordered and nobody else writes these words: plain accumulate
+      p.dlnw[(size_t)bh * 64 + tid] += dgam[tid] + dgam2[tid];
+      p.dlnb[(size_t)bh * 64 + tid] += dbet[tid] + dbet2[tid];
     }
   }
   TICK(16);  // epilogue stores
@@ -646,6 +663,24 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// Upstream gradient of the FINAL state (sequence-sharded chain: the next shard's d/dW_init) -> carried-gradient scratch in
+// the kernel's layout (dW1 transposed to [hidden][F]); one block per sequence.
+__global__ void seed_state_grad_kernel(const float* __restrict__ dW1u, const float* __restrict__ db1u,
+                                       const float* __restrict__ dW2u, const float* __restrict__ db2u, float* dW1s,
+                                       float* dW2s, float* db1s, float* db2s) {
+  const size_t bh = blockIdx.x;
+  __shared__ float tile[64][65];
+  for (int jb = 0; jb < HID; jb += 64) {  // dW1u [F][HID] -> dW1s [HID][F]
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) tile[i >> 6][i & 63] = dW1u[(bh * F + (i >> 6)) * HID + jb + (i & 63)];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) dW1s[(bh * HID + jb + (i >> 6)) * F + (i & 63)] = tile[i & 63][i >> 6];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < HID * F; i += blockDim.x) dW2s[bh * HID * F + i] = dW2u[bh * HID * F + i];
+  for (int i = threadIdx.x; i < HID; i += blockDim.x) db1s[bh * HID + i] = db1u[bh * HID + i];
+  for (int i = threadIdx.x; i < F; i += blockDim.x) db2s[bh * F + i] = db2u[bh * F + i];
+}
+
 }  // namespace bwd
 
 // ------------------------------------------------------------------------------------------------ host
@@ -659,7 +694,7 @@ constexpr int kSuper = 1;
 
 size_t mlp_backward_workspace_bytes(int B, int H, int G) {
   const size_t bh = (size_t)B * H, g = (size_t)G * kSuper, slots = g + 1;
-  return bh * (kRing * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + kRing * (g * 73728 + g * 1024 + g * 256) +
+  return bh * (kRing * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + kRing * (g * 73728 + g * 1024 + g * 768) +
                2 * 65536 + 1024 + 256 + 32768) + 1024;
 }
 
@@ -667,7 +702,9 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
                                 const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
                                 const float* b2c, const void* dOut, float* dlnw, float* dlnb, float* dW1, float* db1,
                                 float* dW2, float* db2, void* dEta, void* dXQ, void* dXK, void* dXV, void* workspace,
-                                size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream) {
+                                size_t workspace_bytes, int B, int H, int NC, int G, cudaStream_t stream,
+                                const float* dW1_last, const float* db1_last, const float* dW2_last,
+                                const float* db2_last) {
   if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) { g_where = "bad sizes"; return cudaErrorInvalidValue; }
   if (workspace_bytes < mlp_backward_workspace_bytes(B, H, G)) { g_where = "workspace"; return cudaErrorInvalidValue; }
   const int Gs = G * kSuper;  // steps per ring buffer = stride of the per-step scratch arrays
@@ -686,7 +723,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   uint8_t* qt[kRing]; float *qb1[kRing], *qb2[kRing];   // Q-side factor tiles / vectors of a group
   for (int i = 0; i < kRing; ++i) { qt[i] = w; w += bh * (size_t)Gs * 73728; }
   for (int i = 0; i < kRing; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 1024; }
-  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 256; }
+  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 768; }
 
   CUtensorMap tq, tk, tv, tdo;
   const uint64_t rows = (uint64_t)bh * NC * 64;
@@ -753,11 +790,16 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     if (e != cudaSuccess) return e;
     if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;
-    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[r], b1img[r], b2img[r], qt[r], qb1[r], qb2[r], dXQ, dlnw, dlnb,
+    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[r], b1img[r], b2img[r], qt[r], qb1[r], qb2[r], dXQ,
                               (int)bh, H, NC, (int)slots, Gs, t0, t1 - t0, sd.sQ);
     if (e != cudaSuccess) return e;
     return cudaEventRecord(sd.evQ[r], sd.sQ);
   };
+  const bool seeded = dW1_last != nullptr;
+  if (seeded) {  // carried gradient starts from the upstream d/dW_last instead of zero
+    bwd::seed_state_grad_kernel<<<(unsigned)bh, 256, 0, stream>>>(dW1_last, db1_last, dW2_last, db2_last, dW1s, dW2s, db1s, db2s);
+    TB_TRY(cudaGetLastError(), "seed launch");
+  }
   TB_TRY(cudaEventRecord(sd.fork, stream), "fork record");
   TB_TRY(cudaStreamWaitEvent(sd.sT, sd.fork, 0), "fork wait");
   TB_TRY(cudaStreamWaitEvent(sd.sQ, sd.fork, 0), "fork wait");
@@ -782,7 +824,7 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     p.H = H; p.NC = NC; p.img_slots = (int)slots;
     p.t_hi = t1 - 1;
     p.t_lo = t0; p.t0 = t0;
-    p.first = (u == 0) ? 1 : 0;
+    p.first = (u == 0 && !seeded) ? 1 : 0;
     p.dbg_group = dbg_group_env;
     p.dbg = g_timing_buf;  // observers: the launch whose t_lo / G equals TTT_DBG_GROUP; per-launch stamps are kept
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);

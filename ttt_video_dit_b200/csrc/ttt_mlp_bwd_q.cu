@@ -37,9 +37,8 @@ struct BwdQParams {
   const uint8_t* img;            // [BH][img_slots] x 64 KB
   const float *b1img, *b2img;    // [BH][img_slots][256], [BH][img_slots][64]
   uint8_t* qt;                   // out: [BH][G] x 73728 B  { Xbar2^T 32 KB, dZbar1^T 32 KB, dZbar2 8 KB }
-  float *qb1, *qb2;              // out: [BH][G][256], [BH][G][64]   (sum_i dZbar1, sum_i dZbar2)
+  float *qb1, *qb2;              // out: [BH][G][256] (sum_i dZbar1), [BH][G][192] = {sum_i dZbar2, d gamma, d beta of the step}
   __nv_bfloat16* dXQ;            // out
-  float *dlnw, *dlnb;            // [BH][64] accumulated with atomics
   int H, NC, img_slots, G, t0;   // step s = t0 + blockIdx.x uses image slot blockIdx.x + 1
 };
 
@@ -236,9 +235,12 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     bulk_commit();
   }
   if (tid < 64) {
-    p.qb2[((size_t)bh * p.G + sl) * 64 + tid] = cb2[tid];
-    atomicAdd(&p.dlnw[(size_t)bh * 64 + tid], cgam[tid]);
-    atomicAdd(&p.dlnb[(size_t)bh * 64 + tid], cbet[tid]);
+    // per-step partials, added by the sequential K-side kernel in step order (no global atomics: the LayerNorm parameter
+    // gradients are bitwise reproducible); the shared-memory sums above start from zero and take exactly two addends
+    float* q2 = p.qb2 + ((size_t)bh * p.G + sl) * 192;
+    q2[tid] = cb2[tid];
+    q2[64 + tid] = cgam[tid];
+    q2[128 + tid] = cbet[tid];
   }
   MMA_WAIT();
   // ===== Q8 [T]: dQ = dO + dQ_u
@@ -261,7 +263,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo, const float* ln_w, const float* ln_b,
                                   const uint8_t* img, const float* b1img, const float* b2img, uint8_t* qt, float* qb1,
-                                  float* qb2, void* dXQ, float* dlnw, float* dlnb, int BH, int H, int NC, int img_slots,
+                                  float* qb2, void* dXQ, int BH, int H, int NC, int img_slots,
                                   int G, int t0, int nsteps, cudaStream_t stream) {
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
   bool& attr_done = *device_once(attr_done_dev);
@@ -271,7 +273,7 @@ cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo,
   }
   bwd::BwdQParams p{};
   p.ln_w = ln_w; p.ln_b = ln_b; p.img = img; p.b1img = b1img; p.b2img = b2img;
-  p.qt = qt; p.qb1 = qb1; p.qb2 = qb2; p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dlnw = dlnw; p.dlnb = dlnb;
+  p.qt = qt; p.qb1 = qb1; p.qb2 = qb2; p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ);
   p.H = H; p.NC = NC; p.img_slots = img_slots; p.G = G; p.t0 = t0;
   dim3 grid(nsteps, BH);
   bwd::ttt_mlp_bwd_q_kernel<<<grid, 256, bwd::QS_TOTAL, stream>>>(tq, tdo, p);

@@ -45,7 +45,7 @@ def linear_forward(XQ, XK, XV, last_eta, ln_w, ln_b, W1, b1, checkpoint_group_si
     b1l = torch.empty(B, H, 1, F, device=dev, dtype=torch.float32) if want_last else None
     p = _lib.ptr
     code = _lib.lib().ttt_b200_linear_forward(p(XQ), p(XK), p(XV), p(le), p(lw), p(lb), p(W1f), p(b1f), p(W1c), p(b1c),
-                                              p(W1l), p(b1l), p(out), B, H, NC, G, _lib.current_stream())
+                                              p(W1l), p(b1l), p(out), B, H, NC, G, _lib.current_stream(XQ))
     _lib.check(code, "ttt_b200_linear_forward")
     return out, (W1c, b1c), ((W1l, b1l) if want_last else None)
 
@@ -74,7 +74,7 @@ def linear_backward(XQ, XK, XV, last_eta, ln_w, ln_b, W1c, b1c, dOut, checkpoint
     p = _lib.ptr
     code = L.ttt_b200_linear_backward(p(XQ), p(XK), p(XV), p(le), p(lw), p(lb), p(W1c), p(b1c), p(go), p(dlw), p(dlb),
                                       p(dW1), p(db1), p(de), p(dq), p(dk), p(dv), p(ws), nbytes, B, H, NC, G,
-                                      _lib.current_stream())
+                                      _lib.current_stream(XQ))
     _lib.check(code, "ttt_b200_linear_backward")
     return dlw.sum(0), dlb.sum(0), dW1, db1, dq, dv, dk, de
 

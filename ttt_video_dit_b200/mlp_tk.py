@@ -48,7 +48,9 @@ def _forward_impl(ctx, ttt_norm_weight, ttt_norm_bias, W1_init, b1_init, W2_init
     lb = ttt_norm_bias.detach().reshape(1, NH, 1, F).to(torch.float32).contiguous()
     ttt_native.ttt_forward(XQ, XK, XV, last_eta, lw, lb, W1, b1, W2, b2, W1c, b1c, W2c, b2c, out, G)
     if ctx is not None:
-        ctx.save_for_backward(XQ, XV, XK, last_eta, lw, lb, W1c, b1c, W2c, b2c, out)
+        # the forward output is NOT saved: the native backward recomputes everything from the checkpoints (the
+        # reference pins it, mlp_tk.py:146-150 -- 2 GB per layer-direction at 63 s for nothing)
+        ctx.save_for_backward(XQ, XV, XK, last_eta, lw, lb, W1c, b1c, W2c, b2c)
         ctx.group = G
     return out
 
@@ -57,7 +59,7 @@ def _backward_impl(ctx, grad_out):
     """mlp_tk.py:154-294 (_backward_core).  Returns grads for (ln_w, ln_b, W1, b1, W2, b2, XQ, XV, XK, last_eta)."""
     if not HAVE_BACKWARD:
         raise RuntimeError("ttt_b200 backward kernel is not available in this build")
-    XQ, XV, XK, last_eta, lw, lb, W1c, b1c, W2c, b2c, out = ctx.saved_tensors
+    XQ, XV, XK, last_eta, lw, lb, W1c, b1c, W2c, b2c = ctx.saved_tensors
     return ttt_native.ttt_backward_simple(XQ, XK, XV, last_eta, lw, lb, W1c, b1c, W2c, b2c,
                                           grad_out.to(torch.bfloat16).contiguous(), ctx.group)
 
@@ -67,6 +69,11 @@ class _TTTMLPLastEta(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ln_w, ln_b, W1, b1, W2, b2, XQ, XV, XK, last_eta, G):
+        if last_eta.numel() != XQ.shape[0] * XQ.shape[1] * XQ.shape[2] * XQ.shape[3]:
+            raise RuntimeError(f"last_eta must hold one value per token: expected [B,H,NC,CS] = {tuple(XQ.shape[:4])} "
+                               f"(any shape with that many elements), got {tuple(last_eta.shape)}")
+        if not last_eta.is_floating_point():
+            raise RuntimeError(f"last_eta must be a floating-point tensor, got {last_eta.dtype}")
         le = last_eta.to(torch.bfloat16).reshape(*XQ.shape[:4], 1).contiguous()
         ctx.eta_shape = last_eta.shape
         return _forward_impl(ctx, ln_w, ln_b, W1, b1, W2, b2, XQ, XV, XK, le, G)

@@ -29,7 +29,7 @@ def _prepare_fwd(xq, xk, xv, lr_logit, rope_cos, rope_sin, ln_w, ln_b, seq_text_
     p = _lib.ptr
     code = _lib.lib().ttt_b200_process_input(p(xq), p(xk), p(xv), p(lg), p(c), p(s), p(lw), p(lb), p(idx), p(XQ), p(XK), p(XV),
                                              p(eta), B, L, H, int(seq_text_length), int(mini_batch_size), float(ttt_base_lr),
-                                             _lib.current_stream())
+                                             _lib.current_stream(xq))
     _lib.check(code, "ttt_b200_process_input")
     return (XQ, XK, XV, eta), (lg, c, s, lw, idx)
 
@@ -61,7 +61,7 @@ class _Prepare(torch.autograd.Function):
         p = _lib.ptr
         code = _lib.lib().ttt_b200_process_input_backward(p(xq), p(xk), p(xv), p(lg), p(c), p(s), p(lw), p(idx), p(gQ), p(gK),
                                                           p(gV), p(ge), p(gxq), p(gxk), p(gxv), p(glg), p(glw), p(glb), B, L, H,
-                                                          seq_text, CS, base_lr, _lib.current_stream())
+                                                          seq_text, CS, base_lr, _lib.current_stream(xq))
         _lib.check(code, "ttt_b200_process_input_backward")
         return (gxq, gxk, gxv, glg.to(lg_dt), glw.reshape(lw_shape).to(lw_dt), glb.reshape(lb_shape).to(lb_dt),
                 None, None, None, None, None, None)
@@ -102,7 +102,7 @@ class _OutputNorm(torch.autograd.Function):
         idx = None if undo_index is None else undo_index.to(device=dev, dtype=torch.int32).contiguous()
         out = torch.empty(B, L, H * 64, device=dev, dtype=torch.bfloat16)
         p = _lib.ptr
-        code = _lib.lib().ttt_b200_output_norm(p(op_out), p(g), p(bt), p(idx), p(out), B, L, H, float(eps), _lib.current_stream())
+        code = _lib.lib().ttt_b200_output_norm(p(op_out), p(g), p(bt), p(idx), p(out), B, L, H, float(eps), _lib.current_stream(op_out))
         _lib.check(code, "ttt_b200_output_norm")
         ctx.save_for_backward(op_out, g, *(() if idx is None else (idx,)))
         ctx.cfg = (float(eps), idx is not None, post_norm_weight.dtype, post_norm_bias.dtype)
@@ -120,7 +120,7 @@ class _OutputNorm(torch.autograd.Function):
         db = torch.empty(H * 64, device=op_out.device, dtype=torch.float32)
         p = _lib.ptr
         code = _lib.lib().ttt_b200_output_norm_backward(p(op_out), p(g), p(idx), p(gout), p(gop), p(dg), p(db), B, NC * CS, H, eps,
-                                                        _lib.current_stream())
+                                                        _lib.current_stream(op_out))
         _lib.check(code, "ttt_b200_output_norm_backward")
         return gop, dg.to(w_dt), db.to(b_dt), None, None
 

@@ -31,7 +31,7 @@ class GatedResidual(torch.autograd.Function):
         rev = torch.empty_like(res) if want_rev else None
         code = _lib.lib().ttt_b200_gate_forward(_lib.ptr(res), _lib.ptr(s), _lib.ptr(at), _lib.ptr(av), _lib.ptr(out),
                                                 _lib.ptr(rev), B, L, E, int(text_len), int(num_chunks), int(perm_s),
-                                                _lib.current_stream())
+                                                _lib.current_stream(res))
         _lib.check(code, "ttt_b200_gate_forward")
         ctx.save_for_backward(s, at, av)
         ctx.meta = (int(text_len), int(num_chunks), int(perm_s), a_text.dtype)
@@ -49,7 +49,7 @@ class GatedResidual(torch.autograd.Function):
         dat = torch.empty(E, device=s.device, dtype=torch.float32); dav = torch.empty_like(dat)
         code = _lib.lib().ttt_b200_gate_backward(_lib.ptr(dout), _lib.ptr(drev), _lib.ptr(s), _lib.ptr(at), _lib.ptr(av),
                                                  _lib.ptr(dres), _lib.ptr(ds), _lib.ptr(dat), _lib.ptr(dav), B, L, E,
-                                                 text_len, num_chunks, perm_s, _lib.current_stream())
+                                                 text_len, num_chunks, perm_s, _lib.current_stream(dout))
         _lib.check(code, "ttt_b200_gate_backward")
         return dres, ds, dat.to(adt), dav.to(adt), None, None, None, None
 

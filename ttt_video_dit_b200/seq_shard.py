@@ -70,6 +70,18 @@ def default_head_groups(B: int, H: int, sms: int = 148) -> int:
     return max(1, min(H, (B * H) // sms))
 
 
+def chain_neighbors(rank: int, world: int, direction: int, group=None):
+    """(previous, next) peer of chain position ``rank`` as GLOBAL ranks (what dist.isend / irecv take), None at the ends.
+    ``rank`` / ``world`` are positions inside ``group`` (the sequence-parallel group of a larger job); messages of one
+    pair are matched by issue order only -- NCCL ignores tags."""
+    chain = list(range(world)) if direction > 0 else list(range(world - 1, -1, -1))
+    pos = chain.index(rank)
+    to_global = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    prev_rank = to_global(chain[pos - 1]) if pos > 0 else None
+    next_rank = to_global(chain[pos + 1]) if pos + 1 < world else None
+    return prev_rank, next_rank
+
+
 def sharded_scan(scan_fn: Callable, q, k, v, last_eta, init_state, *, rank: int, world: int, n_groups: int = None,
                  direction: int = +1, group=None):
     """Run this rank's range of the scan.  q,k,v: [B,H,NC_local,CS,F]; last_eta: [B,H,NC_local,CS,1];
@@ -79,33 +91,27 @@ def sharded_scan(scan_fn: Callable, q, k, v, last_eta, init_state, *, rank: int,
     B, H = q.shape[:2]
     if n_groups is None:
         n_groups = default_head_groups(B, H)
-    chain = list(range(world)) if direction > 0 else list(range(world - 1, -1, -1))
-    pos = chain.index(rank)
-    prev_rank = chain[pos - 1] if pos > 0 else None
-    next_rank = chain[pos + 1] if pos + 1 < world else None
+    prev_rank, next_rank = chain_neighbors(rank, world, direction, group)
     groups = head_groups(H, n_groups)
     out = torch.empty_like(q)
-    recv_bufs, recv_work = [], []
-    if prev_rank is not None:  # post every receive up front: the chain then runs at the pace of the slowest stage
-        for g in groups:
-            buf = torch.empty(B, g.stop - g.start, STATE_NUMEL, dtype=torch.float32, device=q.device)
-            recv_bufs.append(buf)
-            recv_work.append(dist.irecv(buf, src=prev_rank, group=group, tag=g.start))
     sends = []
     finals = []
     for gi, g in enumerate(groups):
         if prev_rank is None:
             st = tuple(t[:, g].contiguous() for t in init_state)
         else:
-            recv_work[gi].wait()
-            st = unpack_state(recv_bufs[gi])
+            # receive of group gi is posted when it is needed (not all up front): NCCL runs the p2p operations of one
+            # communicator in issue order, so a receive posted early would sit in front of this rank's own sends
+            buf = torch.empty(B, g.stop - g.start, STATE_NUMEL, dtype=torch.float32, device=q.device)
+            dist.irecv(buf, src=prev_rank, group=group).wait()
+            st = unpack_state(buf)
         args = (q[:, g].contiguous(), k[:, g].contiguous(), v[:, g].contiguous(), last_eta[:, g].contiguous(), st)
         # per-head parameters (the LayerNorm weight / bias) live in the scan_fn: tell it which heads this call covers
         o, st_out = scan_fn(*args, heads=g) if getattr(scan_fn, "takes_heads", False) else scan_fn(*args)
         out[:, g] = o
         if next_rank is not None:
             buf = pack_state(st_out)
-            sends.append((dist.isend(buf, dst=next_rank, group=group, tag=g.start), buf))
+            sends.append((dist.isend(buf, dst=next_rank, group=group), buf))
         else:
             finals.append(st_out)
     for w, _ in sends:
@@ -138,3 +144,112 @@ def cuda_scan_fn(ln_w, ln_b, checkpoint_group_size=1 << 30):
         return out, tuple(last)
     fn.takes_heads = True
     return fn
+
+
+# ------------------------------------------------------------------------------------------------ training through the chain
+class CudaMLPRange:
+    """Forward + backward of ONE mini-batch range of one (micro-)batch on the sm_100a kernels: the forward writes the fp32
+    checkpoints and exports the final state (the forward hand-off message); the backward takes the upstream gradient of that
+    final state (ttt_b200_mlp_backward_seeded) and returns the gradient of the state it started from (the backward
+    hand-off message)."""
+
+    def __init__(self, ln_w, ln_b, checkpoint_group_size=16):
+        self.ln_w, self.ln_b = ln_w.reshape(-1, 64), ln_b.reshape(-1, 64)
+        self.G = int(checkpoint_group_size)
+
+    def forward(self, q, k, v, last_eta, state):
+        from . import test_time_training as tt
+        B, H, NC = q.shape[:3]
+        dev, f32 = q.device, torch.float32
+        G = min(self.G, NC)
+        K = (NC + G - 1) // G
+        out = torch.empty_like(q)
+        ck = [torch.empty(B, H, K, a, b, device=dev, dtype=f32) for a, b in STATE_SHAPES]
+        last = [torch.empty(B, H, a, b, device=dev, dtype=f32) for a, b in STATE_SHAPES]
+        lw = self.ln_w.reshape(1, H, 1, 64).float().contiguous()
+        lb = self.ln_b.reshape(1, H, 1, 64).float().contiguous()
+        le = last_eta.reshape(B, H, NC, 64, 1)
+        tt.ttt_forward(q, k, v, le, lw, lb, *[s.float().contiguous() for s in state], *ck, out, G, W_last=last)
+        return out, tuple(last), (q, k, v, le, lw, lb, ck, G)
+
+    def backward(self, ctx, grad_out, d_state_out):
+        from . import test_time_training as tt
+        q, k, v, le, lw, lb, ck, G = ctx
+        dlw, dlb, dW1, db1, dW2, db2, dq, dv, dk, de = tt.ttt_backward_simple(q, k, v, le, lw, lb, *ck, grad_out, G,
+                                                                                dW_last=d_state_out)
+        return dq, dk, dv, de, (dW1, db1, dW2, db2), dlw, dlb
+
+
+class ShardedTTTMLP:
+    """This rank's stage of the sequence-sharded TTT-MLP scan, trainable: forward state hand-off down the chain, gradient
+    of the state handed back up the chain.  ``items`` are independent (micro-)batches -- different sequences -- each rank
+    holding ITS mini-batch range of every one of them; because sends are asynchronous the ranks form a pipeline over the
+    items (rank r works on item m while rank r+1 works on item m-1), so with M items in flight the serial chain is busy
+    M / (M + world - 1) of the time (the hand-off itself is 6.35 MB per item and boundary).
+
+    ``impl`` provides forward(q,k,v,last_eta,state) -> (out, state_out, ctx) and backward(ctx, grad_out, d_state_out) ->
+    (dq, dk, dv, d_eta, d_state_in, d_ln_w, d_ln_b): CudaMLPRange in the product, the oracle in the CPU gloo tests."""
+
+    def __init__(self, impl, *, rank: int, world: int, direction: int = +1, group=None):
+        self.impl, self.group = impl, group
+        self.prev, self.next = chain_neighbors(rank, world, direction, group)
+        self._ctx = []
+        self._pending = []  # (work, buffer) of sends not yet known to be complete
+
+    def _recv_state(self, B, H, device, src):
+        buf = torch.empty(B, H, STATE_NUMEL, dtype=torch.float32, device=device)
+        dist.irecv(buf, src=src, group=self.group).wait()
+        return unpack_state(buf)
+
+    def _send_state(self, state, dst):
+        buf = pack_state(state)
+        self._pending.append((dist.isend(buf, dst=dst, group=self.group), buf))
+
+    def _drain(self):
+        for w, _ in self._pending:
+            w.wait()
+        self._pending = []
+
+    def forward(self, items, init_state):
+        """items: list of (q, k, v, last_eta) local ranges [B,H,NC_local,CS,F] / [B,H,NC_local,CS]; init_state: (W1,b1,W2,b2)
+        [B,H,...], read by the first rank of the chain only.  Returns (outs, final_states or None): final_states (one per
+        item) only on the last rank of the chain."""
+        outs, finals = [], []
+        self._ctx = []
+        for q, k, v, le in items:
+            B, H = q.shape[:2]
+            st = tuple(t.contiguous() for t in init_state) if self.prev is None else self._recv_state(B, H, q.device, self.prev)
+            out, st_out, ctx = self.impl.forward(q, k, v, le, st)
+            self._ctx.append(ctx)
+            outs.append(out)
+            if self.next is not None:
+                self._send_state(st_out, self.next)
+            else:
+                finals.append(st_out)
+        self._drain()
+        return outs, (finals if self.next is None else None)
+
+    def backward(self, grad_outs, d_final_states=None):
+        """grad_outs: one upstream gradient per item (layout of the outputs).  d_final_states: optional per-item upstream
+        gradient of the final state, last rank of the chain only (zero at the reference's op boundary).  Returns
+        (item_grads = [(dq, dk, dv, d_last_eta)], d_init_state or None, d_ln_w, d_ln_b): d_init_state (summed over items: the
+        gradient of the shared initial-state parameters) only on the first rank of the chain; d_ln_* are this rank's
+        partial sums (sum them over the ranks of the chain)."""
+        item_grads, d_init, dlw, dlb = [], None, None, None
+        for m, go in enumerate(grad_outs):
+            B, H = go.shape[:2]
+            if self.next is not None:
+                d_out_state = self._recv_state(B, H, go.device, self.next)
+            else:
+                d_out_state = None if d_final_states is None else d_final_states[m]
+            dq, dk, dv, de, d_in, a, b = self.impl.backward(self._ctx[m], go, d_out_state)
+            self._ctx[m] = None
+            item_grads.append((dq, dk, dv, de))
+            dlw = a if dlw is None else dlw + a
+            dlb = b if dlb is None else dlb + b
+            if self.prev is not None:
+                self._send_state(d_in, self.prev)
+            else:
+                d_init = tuple(d_in) if d_init is None else tuple(x + y for x, y in zip(d_init, d_in))
+        self._drain()
+        return item_grads, d_init, dlw, dlb

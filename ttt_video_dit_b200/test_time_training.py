@@ -53,7 +53,7 @@ def ttt_forward(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1, b1, W2
     code = _lib.lib().ttt_b200_mlp_forward(
         p(XQ), p(XK), p(XV), p(last_eta), p(ttt_norm_weight), p(ttt_norm_bias), p(W1), p(b1), p(W2), p(b2),
         p(W1_checkpoints), p(b1_checkpoints), p(W2_checkpoints), p(b2_checkpoints),
-        p(wl[0]), p(wl[1]), p(wl[2]), p(wl[3]), p(Out), B, H, NC, int(checkpoint_group_size), _lib.current_stream())
+        p(wl[0]), p(wl[1]), p(wl[2]), p(wl[3]), p(Out), B, H, NC, int(checkpoint_group_size), _lib.current_stream(XQ))
     _lib.check(code, "ttt_b200_mlp_forward")
     return Out
 
@@ -72,26 +72,21 @@ def launches_bwd():
     return 3 * units
 
 
-_ws_cache = {}
-
-
 def _workspace(B, H, G, device):
-    """Recompute workspace, cached per (device, stream): calls on one stream are ordered, so they can share it; a call on
-    another stream gets its own (the torch allocator only orders reuse within the allocating stream)."""
+    """Recompute workspace of one backward call.  Allocated per call from torch's caching allocator (which makes the
+    reuse cheap and stream-ordered): nothing is pinned for the life of the process, and the block returns to the
+    allocator as soon as the call's tensors die.  Safe with the orchestrator's side streams: every side-stream kernel
+    of a call is consumed by a later main-stream kernel of the same call, so main-stream order covers them."""
     n = _lib.lib().ttt_b200_mlp_backward_workspace_bytes(B, H, G)
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() != n:
-        if len(_ws_cache) >= 4:
-            _ws_cache.clear()
-        ws = _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=device)
-    return ws, n
+    return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
 def ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkpoints, b1_checkpoints,
-                        W2_checkpoints, b2_checkpoints, grad_out, checkpoint_group_size):
+                        W2_checkpoints, b2_checkpoints, grad_out, checkpoint_group_size, dW_last=None):
     """Backward with our own buffer management.  Returns, in TkMLP.backward order (mlp_tk.py:282-294):
-    (d ln_w [H,F], d ln_b [H,F], dW1 [B,H,F,4F], db1 [B,H,1,4F], dW2, db2, dXQ, dXV, dXK, d last_eta [B,H,NC,CS,1])."""
+    (d ln_w [H,F], d ln_b [H,F], dW1 [B,H,F,4F], db1 [B,H,1,4F], dW2, db2, dXQ, dXV, dXK, d last_eta [B,H,NC,CS,1]).
+    ``dW_last`` (extension): optional (dW1, db1, dW2, db2) fp32 = upstream gradient of the FINAL state -- zero in the
+    reference (mlp_tk.py:179-182); the backward hand-off message of the sequence-sharded chain (seq_shard.py)."""
     B, H, NC, CS, F = XQ.shape
     dev = XQ.device
     f32, bf = torch.float32, torch.bfloat16
@@ -105,11 +100,18 @@ def ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1
     de = torch.empty(B, H, NC, CS, 1, device=dev, dtype=bf)
     ws, n = _workspace(B, H, checkpoint_group_size, dev)
     p = _lib.ptr
-    code = _lib.lib().ttt_b200_mlp_backward(
+    up = [None] * 4
+    if dW_last is not None:
+        up = [t.to(f32).contiguous() for t in dW_last]
+        for t, nm, shp in zip(up, ("dW1_last", "db1_last", "dW2_last", "db2_last"),
+                              ((B, H, F, 4 * F), (B, H, 1, 4 * F), (B, H, 4 * F, F), (B, H, 1, F))):
+            _chk(t, nm, f32, shp)
+    code = _lib.lib().ttt_b200_mlp_backward_seeded(
         p(XQ), p(XK), p(XV), p(last_eta), p(ttt_norm_weight), p(ttt_norm_bias),
         p(W1_checkpoints), p(b1_checkpoints), p(W2_checkpoints), p(b2_checkpoints), p(grad_out),
+        p(up[0]), p(up[1]), p(up[2]), p(up[3]),
         p(dlw), p(dlb), p(dW1), p(db1), p(dW2), p(db2), p(de), p(dq), p(dk), p(dv), p(ws), n,
-        B, H, NC, int(checkpoint_group_size), _lib.current_stream())
+        B, H, NC, int(checkpoint_group_size), _lib.current_stream(XQ))
     _lib.check(code, "ttt_b200_mlp_backward")
     _last_groups[0] = K
     return dlw.sum(0), dlb.sum(0), dW1, db1, dW2, db2, dq, dv, dk, de
@@ -124,11 +126,13 @@ def ttt_backward(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkp
                  grad_L_XQ, grad_L_XK, grad_L_XV, checkpoint_group_size):
     """test_time_training.ttt_backward with the reference's 43-argument signature (test_time_training.cpp:47-91).
     The 16 re-materialisation buffers (args 12-27) are accepted and left untouched: this implementation keeps its
-    recompute state in a private L2-resident workspace.  Gradients are written in place into the caller's buffers
+    recompute state in a private L2-resident workspace.  grad_L_W*_last (zeros in the reference, mlp_tk.py:179-182) seed the
+    carried state gradient.  Gradients are written in place into the caller's buffers
     (the reference accumulates into pre-zeroed buffers, mlp_tk.py:213-225; writing gives the same result)."""
     r = ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1_checkpoints, b1_checkpoints,
                             W2_checkpoints, b2_checkpoints, grad_L_XQW_mini_batch.to(torch.bfloat16).contiguous(),
-                            checkpoint_group_size)
+                            checkpoint_group_size,
+                            dW_last=(grad_L_W1_last, grad_L_b1_last, grad_L_W2_last, grad_L_b2_last))
     B, H = XQ.shape[:2]
     # per-batch LN gradients: the reference buffer is [B,H,1,F]; we already reduced over B -> put the sum in row 0
     grad_L_ttt_norm_weight.zero_(); grad_L_ttt_norm_bias.zero_()
