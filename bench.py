@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- TTT hot path benchmark (contract: see task statement / DESIGN.md "Measurement").
 
-A *step* is one pass of the TTT-MLP op over one batch of synthetic token tensors of the named shape:
-forward scan (+ backward scan when --mode fwdbwd) for ONE layer-direction of CogVideoX-5B
-(48 heads x 64, mini-batch 64).  Default workload = BASELINE.json configs[1]:
-3-second video, L = 18 048 tokens -> NC = 282 mini-batches, B = 1 per GPU.
+A *step* is one pass of the TTT-MLP op (forward scan + backward scan) over one batch of synthetic token tensors for ONE
+layer-direction of CogVideoX-5B (48 heads x 64, mini-batch 64, checkpoint group 16).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fwd|fwdbwd] [--nc 282] [--batch 1]
-    python bench.py --impl reference ...      # the reference's eager CPU path (oracle port) on the host cores
+  N = 1 (default)   workload = the 63-second video of BASELINE.json's metric: NC = 5 487 mini-batches (L = 351 168 tokens),
+                    B = 1.  Secondary key "nc804": the same at the 9-second length (the metric's other quoted point).
+  N > 1 (torchrun)  the north-star multi-GPU mode: the sequence is SHARDED over the N ranks (contiguous mini-batch ranges,
+                    ttt_video_dit_b200.seq_shard.ShardedTTTMLP); the only data-path collective is the NCCL send/recv of the
+                    fp32 state {W1,b1,W2,b2} (forward) and of its gradient (backward) at the shard boundaries.  M = 4N
+                    independent sequences are in flight so the serial chain is full (pipeline over sequences); secondary
+                    keys: single-sequence latency through the chain, and plain data-parallel replicas.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fwd|fwdbwd] [--nc 5487] [--batch 1] [--seqs M]
+    python bench.py --impl reference ...      # the reference's eager CPU path on the host cores
 
 value   = tokens/s with inputs resident in HBM (CUDA-event time, max over ranks, whole-job aggregate)
-e2e     = same through the public op with HOST (pinned) inputs: H2D of q,k,v,eta(,dOut) + op + D2H of the result per
-          step, copies double-buffered beside the kernels by ttt_video_dit_b200.host_stream.HostPipeline
-roofline= algorithmic TTT FLOPs (7U fwd, +15U bwd per head per mini-batch, U = 2*64*64*256) / kernel time vs
+e2e     = same through the public op with HOST (pinned) inputs: H2D of q,k,v,eta(,dOut) + op + D2H of the op's output per
+          step, copies placed beside the kernels on copy streams
+roofline= algorithmic TTT FLOPs (7U fwd, +15U bwd per head per mini-batch, U = 2*64*64*256) / op time vs
           MEASURED_PEAKS.json bf16 peak
 """
 import argparse
@@ -30,6 +36,8 @@ os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
 U_FLOP = 2 * 64 * 64 * 256
 FWD_U, BWD_U = 7, 15
 H_5B = 48
+NC_63S, NC_9S, NC_3S = 5487, 804, 282
+CPU_SAMPLE_NC = 64  # time a prefix of >= 64 mini-batches, the scan cost is linear in NC
 
 
 def parse():
@@ -38,12 +46,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "fwd", "fwdbwd"])
-    ap.add_argument("--nc", type=int, default=282, help="mini-batches per sequence (282 = 3 s, 804 = 9 s, 5487 = 63 s)")
+    ap.add_argument("--mode", default="fwdbwd", choices=["auto", "fwd", "fwdbwd"])
+    ap.add_argument("--nc", type=int, default=NC_63S, help="mini-batches per sequence (282 = 3 s, 804 = 9 s, 5487 = 63 s)")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--heads", type=int, default=H_5B)
     ap.add_argument("--ckpt", type=int, default=16)
+    ap.add_argument("--seqs", type=int, default=0, help="N>1: sequences in flight through the sharded chain (default 4N)")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "seqshard", "replicas"],
+                    help="N>1: sequence-sharded chain (default) or independent data-parallel replicas")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary keys (nc804 / latency / replicas)")
     return ap.parse_args()
 
 
@@ -87,91 +99,310 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-_CPU_THREADS = {}
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def usable_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def _eager_once(O, d, mode):
-    import torch
-    t0 = time.perf_counter()
-    if mode == "fwd":
-        with torch.no_grad():
-            O.ttt_mlp_eager(d["XK"], d["XQ"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"])
-    else:
-        O.ttt_mlp_eager_grads(d["XQ"], d["XK"], d["XV"], d["eta"], d["ln_w"], d["ln_b"], d["W1"], d["b1"], d["W2"], d["b2"], d["dOut"])
-    return time.perf_counter() - t0
+class CpuEager:
+    """The reference's eager CPU path of the op on a bounded sample: the real `ttt.models.ssm.ops.ttt_mlp` when
+    /root/reference is importable (kind "reference": the build container), else its restatement oracle/ttt_oracle.py (kind
+    "port": the GPU box, where /root/reference does not exist).  fp32, eta materialised [.., CS, CS] as the reference does
+    (ttt_layer.py:288), autograd backward."""
+
+    def __init__(self, heads, mode, sample_nc=CPU_SAMPLE_NC):
+        import torch
+        from oracle import ttt_oracle as O
+        self.torch, self.mode, self.heads, self.nc = torch, mode, heads, sample_nc
+        self.d = O.make_inputs(1, heads, sample_nc, seed=0)
+        self.kind, self.fn = "port", None
+        ref_root = "/root/reference"
+        if os.path.isdir(os.path.join(ref_root, "ttt", "models", "ssm")):
+            try:
+                sys.path.insert(0, ref_root)
+                from ttt.models.ssm.ops import ttt_mlp as ref_ttt_mlp  # ttt/models/ssm/ops/ttt_mlp.py:70
+                self.kind = "reference"
+                self.fn = lambda k, q, v, e, lw, lb, W1, b1, W2, b2: ref_ttt_mlp(k, q, v, e, lw, lb, W1, b1, W2, b2, 16)
+            except Exception:
+                self.kind, self.fn = "port", None
+            finally:
+                sys.path.remove(ref_root)
+        if self.fn is None:
+            self.fn = lambda *a: O.ttt_mlp_eager(*a)[0]
+
+    def once(self):
+        torch, d = self.torch, self.d
+        names = ("XK", "XQ", "XV", "eta", "ln_w", "ln_b", "W1", "b1", "W2", "b2")
+        t0 = time.perf_counter()
+        if self.mode == "fwd":
+            with torch.no_grad():
+                self.fn(*[d[n] for n in names])
+        else:
+            ins = [d[n].detach().clone().requires_grad_(True) for n in names]
+            out = self.fn(*ins)  # [B,NC,CS,H,F]
+            out.backward(d["dOut"].permute(0, 2, 3, 1, 4))
+        return time.perf_counter() - t0
+
+    def pick_threads(self):
+        """Thread count at which this path is fastest on this host: the ops are small ([heads,64,256] batched matmuls), so
+        'every core' is not the optimum (measured on the 128-core GPU host: 16 threads ~1.5-4 k tok/s, 128 threads 4-150
+        tok/s).  Searched over 1..32 on an 8-mini-batch prefix (the per-mini-batch cost does not depend on the length)."""
+        torch = self.torch
+        cores = usable_cores()
+        cands = sorted({c for c in (1, 2, 4, 8, 16, 32) if c <= cores})
+        full, self.d = self.d, {k: (v[:, :, :8].contiguous() if v.dim() == 5 else v) for k, v in self.d.items()}
+        try:
+            return self._search(cands)
+        finally:
+            self.d = full
+
+    def _search(self, cands):
+        torch = self.torch
+        best_n, best_dt = 1, None
+        for n in cands:
+            torch.set_num_threads(n)
+            self.once()  # thread-pool start-up
+            dt = min(self.once(), self.once())
+            if best_dt is None or dt < best_dt:
+                best_n, best_dt = n, dt
+            elif dt > 2.0 * best_dt:
+                break
+        torch.set_num_threads(best_n)
+        return best_n
+
+    def describe(self, threads):
+        return (f"first {self.nc} mini-batches ({self.nc * 64} tokens) x {self.heads} heads, fp32 eager dual form "
+                f"({'ttt.models.ssm.ops.ttt_mlp of /root/reference' if self.kind == 'reference' else 'oracle port of ttt/models/ssm/ops/ttt_mlp.py'}), "
+                f"{'fwd' if self.mode == 'fwd' else 'fwd + autograd bwd'}, {threads} threads = fastest of 1..{usable_cores()} usable cores, "
+                f"median of the timed passes after one warm-up")
 
 
-def cpu_threads_for_eager(heads, mode):
-    """Thread count at which the eager CPU path is fastest on this host.  The ops are small ([heads,64,256] batched matmuls),
-    so 'every core' is not the optimum (and with a cgroup-limited affinity it oversubscribes): walk 1,2,4,... up to the
-    usable cores, stop once throughput has fallen well below the best seen.  Cached per (heads, mode)."""
-    import torch
-    from oracle import ttt_oracle as O
-    key = (heads, mode)
-    if key in _CPU_THREADS:
-        return _CPU_THREADS[key]
-    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    d = O.make_inputs(1, heads, 2, seed=0)
-    cands, n = [], 1
-    while n < usable:
-        cands.append(n)
-        n *= 2
-    cands.append(usable)
-    best_n, best_dt = 1, None
-    for n in cands:
-        torch.set_num_threads(n)
-        _eager_once(O, d, mode)  # warm-up (thread pool start-up lands here)
-        dt = _eager_once(O, d, mode)
-        if best_dt is not None and dt > 4 * best_dt:  # far past the optimum (oversubscribed): do not spend more time here
-            break
-        dt = min(dt, _eager_once(O, d, mode))
-        if best_dt is None or dt < best_dt:
-            best_n, best_dt = n, dt
-        elif dt > 1.5 * best_dt:
-            break
-    _CPU_THREADS[key] = best_n
-    return best_n
-
-
-def cpu_eager_tokens_per_s(heads, mode, sample_nc=48, reps=2):
-    """The reference's eager path (oracle port of ttt/models/ssm/ops/ttt_mlp.py) on the host cores, fp32, with the thread
-    count that is fastest on this host, on a bounded prefix of the same workload; the scan cost is exactly linear in NC."""
-    import torch
-    from oracle import ttt_oracle as O
-    nthreads = cpu_threads_for_eager(heads, mode)
-    torch.set_num_threads(nthreads)
-    d = O.make_inputs(1, heads, sample_nc, seed=0)
-    best = None
-    for r in range(reps + 1):  # first is warm-up
-        dt = _eager_once(O, d, mode)
-        best = dt if best is None or (r > 0 and dt < best) else best
-    return (sample_nc * 64 / best, best, nthreads,
-            f"first {sample_nc} mini-batches ({sample_nc * 64} tokens) x {heads} heads, fp32 eager dual form, "
-            f"{'fwd' if mode == 'fwd' else 'fwd+autograd bwd'}, {nthreads} threads (fastest of 1..{len(os.sched_getaffinity(0))})")
+def cpu_baseline(heads, mode, reps=3):
+    eager = CpuEager(heads, mode)
+    threads = eager.pick_threads()
+    eager.once()
+    dts = sorted(eager.once() for _ in range(reps))
+    dt = dts[len(dts) // 2]
+    return {"value": eager.nc * 64 / dt, "unit": "tokens/s", "cores": usable_cores(), "threads": threads, "kind": eager.kind,
+            "sample": eager.describe(threads), "seconds_per_pass": dt}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mode = "fwdbwd" if args.mode in ("auto", "fwdbwd") else "fwd"
-    vals = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        v, dt, nthreads, sample = cpu_eager_tokens_per_s(args.heads, mode, sample_nc=16, reps=0)
-        if i >= args.warmup:
-            vals.append((v, dt))
-    tok_s = sum(v for v, _ in vals) / len(vals)
-    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+    mode = "fwd" if args.mode == "fwd" else "fwdbwd"
+    eager = CpuEager(args.heads, mode)
+    threads = eager.pick_threads()
+    for _ in range(args.warmup):
+        eager.once()
+    dts = [eager.once() for _ in range(args.steps)]
+    dt = sum(dts) / len(dts)
+    tok_s = eager.nc * 64 / dt
     line = {
-        "impl": "reference", "metric": "video-tokens/sec TTT-MLP layer-direction (fwd+bwd)" if mode == "fwdbwd" else "video-tokens/sec TTT-MLP layer-direction (fwd)",
-        "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "impl": "reference", "metric": f"video-tokens/sec TTT-MLP layer-direction ({'fwd+bwd' if mode == 'fwdbwd' else 'fwd'})",
+        "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CogVideoX-5B TTT-MLP op, {args.heads} heads x 64, mini-batch 64, NC={args.nc} (sampled)", "mode": mode},
-        "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "config": {"workload": f"CogVideoX-5B TTT-MLP op, {args.heads} heads x 64, mini-batch 64, NC={args.nc} "
+                               f"(each step = the first {eager.nc} mini-batches; the scan is linear in NC)", "mode": mode},
+        "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": usable_cores(), "threads": threads, "kind": eager.kind,
+                         "sample": eager.describe(threads)},
         "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arms
+def synth(torch, dev, B, H, NC, seed, want_dout=True):
+    """Synthetic inputs of SURVEY 8d, generated on the device (63 s = 1.1 G elements per tensor: too slow on the host)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, device=dev)
+    nrm = torch.nn.functional.normalize
+    q = nrm(rn(B, H, NC, 64, 64), dim=-1).to(torch.bfloat16)
+    k = nrm(rn(B, H, NC, 64, 64), dim=-1).to(torch.bfloat16)
+    v = rn(B, H, NC, 64, 64).to(torch.bfloat16)
+    e = ((0.1 / 64) * torch.sigmoid(rn(B, H, NC, 64)) / 64).to(torch.bfloat16)  # the one eta row the scan reads
+    go = rn(B, H, NC, 64, 64).to(torch.bfloat16) if want_dout else None
+    return q, k, v, e, go
+
+
+def synth_params(torch, dev, B, H, seed=99):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, device=dev)
+    ln_w, ln_b = 1 + 0.1 * rn(H, 64), 0.1 * rn(H, 64)
+    W1 = (0.02 * rn(H, 64, 256)).unsqueeze(0).repeat(B, 1, 1, 1).contiguous()
+    W2 = (0.02 * rn(H, 256, 64)).unsqueeze(0).repeat(B, 1, 1, 1).contiguous()
+    return [ln_w, ln_b, W1, torch.zeros(B, H, 1, 256, device=dev), W2, torch.zeros(B, H, 1, 64, device=dev)]
+
+
+def timed(torch, dist, world, fn, steps, warmup, sampler=None):
+    """W warm-up steps, then K steps between barrier + synchronize, CUDA events on the launching stream; returns ms."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if sampler is not None:
+        sampler.stop_flag = True
+    return e0.elapsed_time(e1)
+
+
+def max_over_ranks(torch, dist, world, dev, *vals):
+    t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def single_gpu_op(torch, mlp_tk, params, mode, G):
+    def step(q, k, v, e, go):
+        """One pass of the hot path through the public op (TkMLP.apply-compatible entry, last-row eta form)."""
+        if mode == "fwdbwd":
+            q = q.detach().requires_grad_(True); k = k.detach().requires_grad_(True); v = v.detach().requires_grad_(True)
+        out = mlp_tk.ttt_mlp_op(*params, q, v, k, e, G)
+        if mode == "fwdbwd":
+            out.backward(go)
+        return out
+    return step
+
+
+def bench_replica(args, torch, dist, mlp_tk, world, rank, dev, mode, NC, with_e2e, steps, warmup, sampler=None):
+    """B sequences per GPU, un-sharded: the N = 1 workload, and the data-parallel-replica secondary key at N > 1."""
+    B, H, G = args.batch, args.heads, args.ckpt
+    params = synth_params(torch, dev, B, H)
+    if mode == "fwdbwd":
+        params = [p.requires_grad_(True) for p in params]
+    q, k, v, e, go = synth(torch, dev, B, H, NC, 1234 + rank, mode == "fwdbwd")
+    step = single_gpu_op(torch, mlp_tk, params, mode, G)
+    ms = timed(torch, dist, world, lambda: step(q, k, v, e, go), steps, warmup, sampler)
+    res = {"ms_per_step": ms / steps, "tokens_per_step": B * NC * 64 * world,
+           "launches": steps * mlp_tk.launches_per_call(mode)}
+    if with_e2e:
+        # end to end from pinned host memory.  Every step copies its own inputs host->device and its result device->host inside
+        # the timed region; HostPipeline places H2D(i+1) and D2H(i-1) beside op(i) instead of in front of it.
+        from ttt_video_dit_b200.host_stream import HostPipeline
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        host = [pin(t) if t is not None else None for t in (q, k, v, e, go)]
+        host_out = torch.empty(B, H, NC, 64, 64, dtype=torch.bfloat16, pin_memory=True)
+        h2d = sum(t.numel() * t.element_size() for t in host if t is not None)
+        d2h = host_out.numel() * 2
+        del q, k, v, go
+        pipe = HostPipeline(dev)
+        pipe.run((host for _ in range(2)), step, host_out)
+        torch.cuda.synchronize()
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        n_e2e = max(3, steps // 2) if NC > 1000 else steps  # 63 s: 10.8 GB in + 2.2 GB out per step over PCIe
+        if world > 1:
+            dist.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        n = pipe.run((host for _ in range(n_e2e)), step, host_out)
+        f1.record()
+        torch.cuda.synchronize()
+        assert n == n_e2e and pipe.h2d_bytes == h2d * n_e2e and pipe.d2h_bytes == d2h * n_e2e
+        res.update(e2e_ms_per_step=f0.elapsed_time(f1) / n_e2e, h2d=h2d, d2h=d2h, e2e_steps=n_e2e)
+    return res
+
+
+def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, steps, warmup, sampler=None):
+    """The sequence-sharded chain: this rank owns mini-batch range `rank` of each of the M sequences."""
+    from ttt_video_dit_b200 import seq_shard, test_time_training as tt
+    H, G = args.heads, args.ckpt
+    s, e_ = seq_shard.partition_minibatches(NC, world)[rank]
+    n_local = e_ - s
+    ln_w, ln_b, W1, b1, W2, b2 = synth_params(torch, dev, 1, H)
+    impl = seq_shard.CudaMLPRange(ln_w, ln_b, checkpoint_group_size=G)
+    stage = seq_shard.ShardedTTTMLP(impl, rank=rank, world=world)
+    items, gouts = [], []
+    for m in range(M):
+        q, k, v, e, go = synth(torch, dev, 1, H, n_local, 5000 + 97 * m + rank, True)
+        items.append((q, k, v, e)); gouts.append(go)
+
+    def step():
+        outs, _ = stage.forward(items, (W1, b1, W2, b2))
+        if mode == "fwdbwd":
+            stage.backward(gouts)
+        return outs
+    ms = timed(torch, dist, world, step, steps, warmup, sampler)
+    groups = (n_local + min(G, n_local) - 1) // min(G, n_local)
+    per_item = tt.LAUNCHES_FWD + ((3 * groups + (1 if rank != world - 1 else 0)) if mode == "fwdbwd" else 0)
+    res = {"ms_per_step": ms / steps, "tokens_per_step": M * NC * 64, "launches": steps * M * per_item}
+    if with_e2e:
+        # every step, every item: H2D of this rank's range of q,k,v,eta,dOut from pinned host memory on a copy stream (ahead of
+        # the chain), D2H of the item's output range on a second copy stream.  The pinned source holds ONE item (synthetic
+        # data); each of the M items is a separate copy into its own device buffers.
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        host = [pin(t) for t in (*items[0], gouts[0])]
+        host_out = torch.empty(host[0].shape, dtype=host[0].dtype, pin_memory=True)
+        ev_in = [torch.cuda.Event() for _ in range(M)]
+        ev_done = [torch.cuda.Event() for _ in range(M)]
+        h2d = M * sum(t.numel() * t.element_size() for t in host)
+        d2h = M * host_out.numel() * 2
+        main = torch.cuda.current_stream(dev)
+
+        class Feed:  # the stage's implementation with the copies around it
+            def forward(self, q, k, v, le, st):
+                m = self.m
+                main.wait_event(ev_in[m])
+                out, st_out, ctx = impl.forward(q, k, v, le, st)
+                ev = torch.cuda.Event(); ev.record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev)
+                    host_out.copy_(out, non_blocking=True)
+                    out.record_stream(s_out)
+                self.m += 1
+                return out, st_out, ctx
+
+            def backward(self, ctx, go, d_state):
+                r = impl.backward(ctx, go, d_state)
+                ev_done[self.mb].record(main)
+                self.mb += 1
+                return r
+        feed = Feed()
+        stage_e2e = seq_shard.ShardedTTTMLP(feed, rank=rank, world=world)
+
+        def step_e2e(first=False):
+            with torch.cuda.stream(s_in):
+                for m in range(M):
+                    if not first:
+                        s_in.wait_event(ev_done[m])  # the previous step's backward has consumed item m's buffers
+                    for dst, src in zip((*items[m], gouts[m]), host):
+                        dst.copy_(src, non_blocking=True)
+                    ev_in[m].record(s_in)
+            feed.m = feed.mb = 0
+            stage_e2e.forward(items, (W1, b1, W2, b2))
+            if mode == "fwdbwd":
+                stage_e2e.backward(gouts)
+            else:
+                for m in range(M):
+                    ev_done[m].record(main)
+            main.wait_stream(s_out)
+        s_in.wait_stream(main)
+        step_e2e(first=True)
+        torch.cuda.synchronize()
+        n_e2e = max(3, steps // 2)
+        if world > 1:
+            dist.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(n_e2e):
+            step_e2e()
+        f1.record()
+        torch.cuda.synchronize()
+        res.update(e2e_ms_per_step=f0.elapsed_time(f1) / n_e2e, h2d=h2d * world, d2h=d2h * world, e2e_steps=n_e2e)
+    return res
 
 
 def main():
@@ -195,143 +426,89 @@ def main():
         dist.barrier()
     from ttt_video_dit_b200 import mlp_tk
 
-    have_bwd = mlp_tk.HAVE_BACKWARD
-    mode = args.mode if args.mode != "auto" else ("fwdbwd" if have_bwd else "fwd")
-    if mode == "fwdbwd" and not have_bwd:
-        raise SystemExit("backward kernel not built")
-    B, H, NC, G = args.batch, args.heads, args.nc, args.ckpt
-    L = NC * 64
-
-    # synthetic inputs, generated once on the host, kept pinned for the e2e leg
-    gen = torch.Generator().manual_seed(1234 + rank)
-    rn = lambda *s: torch.randn(*s, generator=gen)
-    XQ = torch.nn.functional.normalize(rn(B, H, NC, 64, 64), dim=-1).to(torch.bfloat16).pin_memory()
-    XK = torch.nn.functional.normalize(rn(B, H, NC, 64, 64), dim=-1).to(torch.bfloat16).pin_memory()
-    XV = rn(B, H, NC, 64, 64).to(torch.bfloat16).pin_memory()
-    eta_last = ((0.1 / 64) * torch.sigmoid(rn(B, H, NC, 1, 64)) / 64).to(torch.bfloat16).pin_memory()  # one row of eta
-    dOut = rn(B, H, NC, 64, 64).to(torch.bfloat16).pin_memory()
-    ln_w = (1 + 0.1 * rn(H, 64)).to(dev)
-    ln_b = (0.1 * rn(H, 64)).to(dev)
-    W1 = (0.02 * rn(H, 64, 256)).unsqueeze(0).repeat(B, 1, 1, 1).to(dev)
-    b1 = torch.zeros(B, H, 1, 256, device=dev)
-    W2 = (0.02 * rn(H, 256, 64)).unsqueeze(0).repeat(B, 1, 1, 1).to(dev)
-    b2 = torch.zeros(B, H, 1, 64, device=dev)
-    params = [ln_w, ln_b, W1, b1, W2, b2]
-    if mode == "fwdbwd":
-        params = [p.requires_grad_(True) for p in params]
-
-    dq, dk, dv, de, dgo = (t.to(dev) for t in (XQ, XK, XV, eta_last, dOut))
-    launches = {"n": 0}
-    kern_ms = []
-
-    def step(q, k, v, e, go, time_kernels=False):
-        """One pass of the hot path through the public op (TkMLP.apply-compatible entry, last-row eta form)."""
-        if mode == "fwdbwd":
-            q = q.detach().requires_grad_(True); k = k.detach().requires_grad_(True); v = v.detach().requires_grad_(True)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if time_kernels else None
-        if ev:
-            ev[0].record()
-        out = mlp_tk.ttt_mlp_op(*params, q, v, k, e, G)
-        if mode == "fwdbwd":
-            out.backward(go)
-        if ev:
-            ev[1].record()
-            kern_ms.append(ev)
-        launches["n"] += mlp_tk.launches_per_call(mode)
-        return out
-
-    for _ in range(args.warmup):
-        step(dq, dk, dv, de, dgo)
-    torch.cuda.synchronize()
-
-    # ---- timed region 1: inputs resident in HBM
+    mode = "fwd" if args.mode == "fwd" else "fwdbwd"
+    H, NC, G = args.heads, args.nc, args.ckpt
+    sharded = world > 1 and args.parallel in ("auto", "seqshard")
+    M = (args.seqs or 4 * world) if sharded else None
     sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches["n"] = 0
-    e0.record()
-    for _ in range(args.steps):
-        step(dq, dk, dv, de, dgo, time_kernels=True)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler.stop_flag = True
-    ms_total = e0.elapsed_time(e1)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kern_ms) / max(1, len(kern_ms))
-    n_launch = launches["n"]
+    if sharded:
+        r = bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, True, args.steps, args.warmup, sampler)
+    else:
+        r = bench_replica(args, torch, dist, mlp_tk, world, rank, dev, mode, NC, True, args.steps, args.warmup, sampler)
+    ms_step, ms_e2e = max_over_ranks(torch, dist, world, dev, r["ms_per_step"], r["e2e_ms_per_step"])
 
-    # ---- timed region 2: end to end from pinned host memory.  Every step copies its own inputs host->device and its
-    # result device->host inside the timed region; ttt_video_dit_b200.host_stream.HostPipeline (the package's host-side
-    # entry for callers that keep tokens in pinned memory) places H2D(i+1) and D2H(i-1) beside op(i) instead of in front.
-    from ttt_video_dit_b200.host_stream import HostPipeline
-    host_out = torch.empty(B, H, NC, 64, 64, dtype=torch.bfloat16).pin_memory()
-    host_batch = (XQ, XK, XV, eta_last, dOut if mode == "fwdbwd" else None)
-    h2d = sum(t.numel() * t.element_size() for t in host_batch if t is not None)
-    d2h = host_out.numel() * 2
-    pipe = HostPipeline(dev)
-    pipe.run((host_batch for _ in range(2)), step, host_out)
-    torch.cuda.synchronize()
-    pipe.h2d_bytes = pipe.d2h_bytes = 0
-    if world > 1:
-        dist.barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    n_e2e = pipe.run((host_batch for _ in range(args.steps)), step, host_out)
-    f1.record()
-    torch.cuda.synchronize()
-    assert n_e2e == args.steps and pipe.h2d_bytes == h2d * args.steps and pipe.d2h_bytes == d2h * args.steps
-    ms_e2e = f0.elapsed_time(f1)
-
-    t = torch.tensor([ms_total, ms_e2e, kernel_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, kernel_ms = [float(x) for x in t]
+    secondary = {}
+    if not args.no_secondary:
+        torch.cuda.empty_cache()
+        if sharded:
+            lat = bench_sharded(args, torch, dist, world, rank, dev, mode, NC, 1, False, 3, 1)
+            (ms_lat,) = max_over_ranks(torch, dist, world, dev, lat["ms_per_step"])
+            secondary["single_sequence"] = {"ms": ms_lat, "tokens_per_s": NC * 64 / (ms_lat * 1e-3),
+                                            "note": "ONE sequence through the N-rank chain (serial recurrence: no speed-up over one "
+                                                    "GPU is possible; this is the latency the hand-offs add)"}
+            torch.cuda.empty_cache()
+            rep = bench_replica(args, torch, dist, mlp_tk, world, rank, dev, mode, NC, False, 3, 1)
+            (ms_rep,) = max_over_ranks(torch, dist, world, dev, rep["ms_per_step"])
+            secondary["replicas"] = {"ms_per_step": ms_rep, "tokens_per_s": rep["tokens_per_step"] / (ms_rep * 1e-3),
+                                     "note": f"dp{world}: independent un-sharded replicas, B={args.batch} per GPU, no data-path collective"}
+        elif NC != NC_9S and world == 1:
+            r9 = bench_replica(args, torch, dist, mlp_tk, world, rank, dev, mode, NC_9S, False, 5, 2)
+            secondary["nc804"] = {"ms_per_step": r9["ms_per_step"], "tokens_per_s": r9["tokens_per_step"] / (r9["ms_per_step"] * 1e-3),
+                                  "note": "the 9-second video (3 interleaved segments, NC = 804), same op and mode"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    tokens_per_step = B * L * world
-    ms_per_step = ms_total / args.steps
-    value = tokens_per_step / (ms_per_step * 1e-3)
-    e2e_val = tokens_per_step / (ms_e2e / args.steps * 1e-3)
-    flop_per_step = B * H * NC * U_FLOP * (FWD_U + (BWD_U if mode == "fwdbwd" else 0))
+    tokens = r["tokens_per_step"]
+    value = tokens / (ms_step * 1e-3)
+    e2e_val = tokens / (ms_e2e * 1e-3)
+    seqs_per_step = M if sharded else args.batch * world
+    flop_per_step = seqs_per_step * H * NC * U_FLOP * (FWD_U + (BWD_U if mode == "fwdbwd" else 0))
     burst, sustained, src = peaks()
-    achieved = flop_per_step / (kernel_ms * 1e-3) / 1e12
+    achieved = flop_per_step / (ms_step * 1e-3) / 1e12 / world  # per GPU
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to one launch
         tj = json.load(open(tpath)).get(mode)
         if tj:
-            per_launch_units = B * H * (NC if mode == "fwd" else min(G, NC))
+            per_launch_units = args.batch * H * (NC if mode == "fwd" else min(G, NC))
             traffic = {"bytes_per_launch": tj["bytes_per_head_minibatch"] * per_launch_units, "kernel": tj["kernel"], "source": tj["source"]}
+    secs = {NC_63S: "63-sec video, 21 segments", NC_9S: "9-sec video, 3 segments", NC_3S: "3-sec segment"}.get(NC, f"{NC} mini-batches")
+    if sharded:
+        par = (f"sequence-sharded x{world}: rank r owns mini-batch range r of every sequence ({NC // world}-{-(-NC // world)} "
+               f"mini-batches); NCCL send/recv of the fp32 state (forward, 6.35 MB per sequence and boundary) and of its gradient "
+               f"(backward) is the only data-path collective; {M} sequences in flight (pipeline over sequences, bubble "
+               f"{(world - 1)}/{(M + world - 1)})")
+    else:
+        par = f"dp{world}: un-sharded replicas, no data-path collective" if world > 1 else "single GPU"
     line = {
         "metric": f"video-tokens/sec TTT-MLP layer-direction ({'fwd+bwd' if mode == 'fwdbwd' else 'fwd'})",
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"CogVideoX-5B TTT-MLP op ({'3-sec' if NC == 282 else str(NC) + ' mini-batch'} segment): B={B}/GPU, "
-                               f"{H} heads x 64, mini-batch 64, NC={NC} (L={L} tokens), checkpoint group {G}, one layer-direction",
-                   "mode": mode, "parallelism": f"dp{world} replicas (no data-path collective)",
-                   "l2": "inputs (q,k,v = %.0f MB) larger than the 126 MB L2; no explicit flush" % (3 * B * H * NC * 8192 / 1e6)},
-        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps,
-                "pipeline": "pinned host -> H2D on a copy stream (prefetch of step i+1 beside op i) -> op -> D2H on a second "
-                            "copy stream; all copies of all steps inside the timed region"},
-        "gpu_launches": n_launch,
+        "config": {"workload": f"CogVideoX-5B TTT-MLP op ({secs}): {seqs_per_step} sequence(s) per step, {H} heads x 64, mini-batch 64, "
+                               f"NC={NC} (L={NC * 64} tokens), checkpoint group {G}, one layer-direction",
+                   "mode": mode, "parallelism": par,
+                   "l2": "inputs (q,k,v = %.0f MB per sequence) larger than the 126 MB L2; no explicit flush" % (3 * H * NC * 8192 / 1e6)},
+        "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": ms_e2e, "steps": r["e2e_steps"],
+                "pipeline": "pinned host -> H2D on a copy stream (ahead of the op) -> op -> D2H of the op's output on a second copy "
+                            "stream; all copies of all steps inside the timed region; in fwd+bwd mode dXQ/dXK/dXV stay on the "
+                            "device (they feed the upstream layer's backward), only the forward output is read back"
+                            + ("; byte counts are whole-job (all ranks)" if world > 1 else "")},
+        "gpu_launches": r["launches"],
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "traffic": traffic, "peak_source": src + ", burst figure (op timed alone)",
-                     "kernel_ms": kernel_ms, "algorithmic_flop_per_step": flop_per_step,
-                     "scope": "whole step (all our kernels of the op: 7U fwd + 15U bwd per head per mini-batch; recompute not counted)"},
+                     "algorithmic_flop_per_step": flop_per_step,
+                     "scope": "whole step, per GPU (all our kernels of the op: 7U fwd + 15U bwd per head per mini-batch; recompute not counted)"},
     }
-    if not args.no_cpu_baseline:
-        v, dt, nthreads, sample = cpu_eager_tokens_per_s(H, mode)
-        line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": nthreads, "kind": "port", "sample": sample}
+    line.update(secondary)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(H, mode)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -30,8 +30,10 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, dbg=False):
+def build(force=False, verbose=False, dbg=False, noelect=False):
     global LIB
+    if noelect:  # A/B variant of the single-lane issue pattern (csrc/ptx.cuh TB_NO_ELECT)
+        return _build(os.path.join(LIBDIR, "libttt_b200_noelect.so"), os.path.join(HERE, "build_noelect"), ["-DTB_NO_ELECT"], verbose)
     if dbg:
         return _build(os.path.join(LIBDIR, "libttt_b200_dbg.so"), os.path.join(HERE, "build_dbg"), ["-DTTT_PHASE_TIMING"], verbose)
     if not force and not needs_build():
@@ -70,4 +72,4 @@ def _build(LIB, objdir, extra, verbose):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dbg="--dbg" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dbg="--dbg" in sys.argv, noelect="--noelect" in sys.argv))

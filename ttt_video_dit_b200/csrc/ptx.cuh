@@ -156,6 +156,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // the descriptors are re-materialised per instruction (scripts/sass_experiments/elect_issue.cu: 12 issue slots per MMA
 // instead of 1).
 #define TB_HAS_ELECT_ONE 1
+#ifndef TB_NO_ELECT
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -163,6 +164,10 @@ __device__ __forceinline__ bool elect_one() {
 }
 // warp index as a value the compiler knows to be warp-uniform
 __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+#else  // A/B build (lib/libttt_b200_noelect.so): the round-1 `if (tid == 0)` issue pattern, for scripts/r02_gpu_check.sh
+__device__ __forceinline__ bool elect_one() { return (threadIdx.x & 31) == 0; }
+__device__ __forceinline__ int uniform_warp_id() { return (int)(threadIdx.x >> 5); }
+#endif
 
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
