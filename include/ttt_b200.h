@@ -160,6 +160,21 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                            const float* alpha_video, void* dres, void* ds, float* d_alpha_text, float* d_alpha_video,
                            int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream);
 
+/* adaLN shell of the DiT TransformerLayer around the hot path (ttt/models/cogvideo/dit.py:321-382).
+ * ln_affine: out[b,l,:] = LayerNorm_noaffine(x[b,l,:]; eps) * A[b,s,:] + C[b,s,:], s = (l < text_len ? 0 : 1) -- replaces
+ * pre_seq_layernorm / pre_mlp_layernorm + modulate(x, shift, scale) (dit.py:344-345,367-368) with the caller folding
+ * A = gamma * (1 + scale), C = beta * (1 + scale) + shift (f32 [B,2,E], text row first).  x/out bf16 [B,L,E], text tokens
+ * first, E % 64 == 0, E <= 4096.  _backward: d_out bf16 -> d_x bf16, d_A / d_C f32 [B,2,E] (overwritten).
+ * gate_add: out = x + G[b,s,:] * y -- the gated residuals emb + gate * block_out (dit.py:349-350,381-382), G f32 [B,2,E];
+ * _backward: d_y = G * d_out (bf16), d_G f32 [B,2,E] = sum over the rows of g * y (overwritten); d_x = d_out. */
+int ttt_b200_ln_affine(const void* x, const float* A, const float* C, void* out, int B, int L, int E, int text_len, float eps,
+                       void* stream);
+int ttt_b200_ln_affine_backward(const void* x, const float* A, const void* d_out, void* d_x, float* d_A, float* d_C, int B, int L,
+                                int E, int text_len, float eps, void* stream);
+int ttt_b200_gate_add(const void* x, const void* y, const float* G, void* out, int B, int L, int E, int text_len, void* stream);
+int ttt_b200_gate_add_backward(const void* d_out, const void* y, const float* G, void* d_y, float* d_G, int B, int L, int E,
+                               int text_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

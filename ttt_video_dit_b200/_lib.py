@@ -31,6 +31,10 @@ _SIGS = {
     "ttt_b200_output_norm_backward": ([_vp, _fp, _vp, _vp, _vp, _fp, _fp] + [_i] * 3 + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_gate_forward": ([_vp, _vp, _fp, _fp, _vp, _vp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_gate_backward": ([_vp, _vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 6 + [_vp], ctypes.c_int),
+    "ttt_b200_ln_affine": ([_vp, _fp, _fp, _vp] + [_i] * 4 + [ctypes.c_float, _vp], ctypes.c_int),
+    "ttt_b200_ln_affine_backward": ([_vp, _fp, _vp, _vp, _fp, _fp] + [_i] * 4 + [ctypes.c_float, _vp], ctypes.c_int),
+    "ttt_b200_gate_add": ([_vp, _vp, _fp, _vp] + [_i] * 4 + [_vp], ctypes.c_int),
+    "ttt_b200_gate_add_backward": ([_vp, _vp, _fp, _vp, _fp] + [_i] * 4 + [_vp], ctypes.c_int),
 }
 
 # development probes (include/ttt_b200_debug.h) live in their own library; the production .so exports none of them

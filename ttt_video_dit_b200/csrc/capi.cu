@@ -201,6 +201,35 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                   "ttt_b200_gate_backward");
 }
 
+int ttt_b200_ln_affine(const void* x, const float* A, const float* C, void* out, int B, int L, int E, int text_len, float eps,
+                       void* stream) {
+  if (!x || !A || !C || !out) return fail(-1, "ttt_b200_ln_affine: null pointer argument");
+  TB_BIND_DEVICE(x);
+  return cuda_ret(tb::launch_ln_affine(x, A, C, out, B, L, E, text_len, eps, (cudaStream_t)stream), "ttt_b200_ln_affine");
+}
+
+int ttt_b200_ln_affine_backward(const void* x, const float* A, const void* d_out, void* d_x, float* d_A, float* d_C, int B, int L,
+                                int E, int text_len, float eps, void* stream) {
+  if (!x || !A || !d_out || !d_x || !d_A || !d_C) return fail(-1, "ttt_b200_ln_affine_backward: null pointer argument");
+  TB_BIND_DEVICE(x);
+  return cuda_ret(tb::launch_ln_affine_backward(x, A, d_out, d_x, d_A, d_C, B, L, E, text_len, eps, (cudaStream_t)stream),
+                  "ttt_b200_ln_affine_backward");
+}
+
+int ttt_b200_gate_add(const void* x, const void* y, const float* G, void* out, int B, int L, int E, int text_len, void* stream) {
+  if (!x || !y || !G || !out) return fail(-1, "ttt_b200_gate_add: null pointer argument");
+  TB_BIND_DEVICE(x);
+  return cuda_ret(tb::launch_gate_add(x, y, G, out, B, L, E, text_len, (cudaStream_t)stream), "ttt_b200_gate_add");
+}
+
+int ttt_b200_gate_add_backward(const void* d_out, const void* y, const float* G, void* d_y, float* d_G, int B, int L, int E,
+                               int text_len, void* stream) {
+  if (!d_out || !y || !G || !d_y || !d_G) return fail(-1, "ttt_b200_gate_add_backward: null pointer argument");
+  TB_BIND_DEVICE(d_out);
+  return cuda_ret(tb::launch_gate_add_backward(d_out, y, G, d_y, d_G, B, L, E, text_len, (cudaStream_t)stream),
+                  "ttt_b200_gate_add_backward");
+}
+
 #ifdef TTT_PHASE_TIMING
 /* phase-timing build only (lib/libttt_b200_dbg.so): device buffer (>= 512 bytes) receiving per-phase cycle counts */
 int ttt_b200_debug_set_timing_buffer(void* dev_buf_512_bytes) {

@@ -279,6 +279,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// fp16 operand tiles (forward-type GEMMs of the TTT-MLP scans: 11-bit mantissa instead of bf16's 8 -- the first mini-batch
+// of a sequence has a LayerNorm std of ~3e-3 and amplifies operand rounding by 1/std, DESIGN.md "operand format")
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float f16_hi(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+// a bf16 pair -> the same two values as an fp16 pair (exact for |x| in [6.1e-5, 65504]; smaller magnitudes keep 2^-24 steps)
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) { return pack_f16(bf16_lo(v), bf16_hi(v)); }
+// operand-format switch of the TTT-MLP forward-type kernels
+template <bool kF16> __device__ __forceinline__ uint32_t pack_op(float lo, float hi) { return kF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+template <bool kF16> __device__ __forceinline__ float op_lo(uint32_t v) { return kF16 ? f16_lo(v) : bf16_lo(v); }
+template <bool kF16> __device__ __forceinline__ float op_hi(uint32_t v) { return kF16 ? f16_hi(v) : bf16_hi(v); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

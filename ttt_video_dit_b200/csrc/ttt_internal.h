@@ -51,10 +51,7 @@ cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float*
 }  // namespace tb
 
 namespace tb {
-cudaError_t launch_mlp_trajectory(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
-                                  const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
-                                  const float* b2c, int B, int H, int NC, int K, int k, int t0, int nsteps,
-                                  uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream);
+bool mlp_operands_bf16();  // TTT_B200_OPERANDS=bf16: bf16 instead of fp16 operand tiles in the forward-type kernels (A/B)
 cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                           const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
                                           const float* b2c, int B, int H, int NC, int K, int G, int t0, int t_end,
@@ -138,4 +135,15 @@ cudaError_t launch_output_norm(const void* O, const float* gamma, const float* b
 namespace tb {
 cudaError_t launch_output_norm_backward(const void* O, const float* gamma, const int* index, const void* gout, void* gO,
                                         float* dgamma, float* dbeta, int B, int L, int H, float eps, cudaStream_t stream);
+}  // namespace tb
+
+namespace tb {
+cudaError_t launch_ln_affine(const void* x, const float* A, const float* C, void* out, int B, int L, int E, int text_len,
+                             float eps, cudaStream_t stream);
+cudaError_t launch_ln_affine_backward(const void* x, const float* A, const void* gout, void* gx, float* dA, float* dC, int B,
+                                      int L, int E, int text_len, float eps, cudaStream_t stream);
+cudaError_t launch_gate_add(const void* x, const void* y, const float* G, void* out, int B, int L, int E, int text_len,
+                            cudaStream_t stream);
+cudaError_t launch_gate_add_backward(const void* gout, const void* y, const float* G, void* dy, float* dG, int B, int L, int E,
+                                     int text_len, cudaStream_t stream);
 }  // namespace tb

@@ -762,12 +762,9 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     }
   }
   const int K = (NC + G - 1) / G;
-  // compact (L1.5-resident) trajectory kernel by default; TTT_B200_TRAJ=legacy runs the forward kernel in trajectory mode
-  // instead (one group per launch; 48 KB loop that disturbs the K-side kernel's instruction fetch)
-  static const bool legacy_traj = [] { const char* v = getenv("TTT_B200_TRAJ"); return v && v[0] == 'l'; }();
   static const int dbg_group_env = [] { const char* v = getenv("TTT_DBG_GROUP"); return v ? atoi(v) : 0; }();
   static const int super_env = [] { const char* v = getenv("TTT_B200_SUPER"); return v ? atoi(v) : kSuper; }();
-  const int m = legacy_traj ? 1 : (super_env < 1 ? 1 : (super_env > kSuper ? kSuper : super_env));
+  const int m = super_env < 1 ? 1 : (super_env > kSuper ? kSuper : super_env);
   // units in processing order (descending steps): {first group, last group}; the first unit is the last group alone
   int ulo[1 + 4096], uhi[1 + 4096], U = 0;
   for (int g = K - 1; g >= 0;) {
@@ -782,11 +779,8 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     const int r = u % kRing;
     const int t0 = ulo[u] * G;
     const int t1 = ((uhi[u] + 1) * G < NC) ? (uhi[u] + 1) * G : NC;
-    cudaError_t e = legacy_traj
-                        ? launch_mlp_trajectory(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, ulo[u], t0, t1 - t0,
-                                                img[r], b1img[r], b2img[r], (int)slots, sd.sT)
-                        : launch_mlp_trajectory_compact(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, G, t0, t1,
-                                                        img[r], b1img[r], b2img[r], (int)slots, sd.sT);
+    cudaError_t e = launch_mlp_trajectory_compact(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, G, t0, t1,
+                                                  img[r], b1img[r], b2img[r], (int)slots, sd.sT);
     if (e != cudaSuccess) return e;
     if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;

@@ -15,6 +15,14 @@
 // The Q side of mini-batch t-1 rides along with the K side of mini-batch t (software pipelining by one step), which
 // makes both "half-size" GEMMs of the recurrence M=128.  bf16 operand copies of W (W1b^T, W2b) are re-materialised
 // from TMEM once per step.  All smem operand tiles use the SW128 row-tile convention of ptx.cuh.
+//
+// Operand format: every MMA operand tile is fp16 by default (template kF16): the state images, X2 / G tiles are produced
+// here and simply packed as f16; the K and Q token tiles arrive as bf16 by TMA and are converted in place (exact) right
+// after landing.  bf16 -> f16 operands cut the operand rounding 8x, which matters because the first mini-batch of a
+// sequence (b2 = 0: LayerNorm std ~3e-3) amplifies it by 1/std into the whole state trajectory, and the gradient of some
+// heads is ill-conditioned w.r.t. that trajectory (measured: 8 % gradient deviation on the worst of 48 heads with bf16
+// operands, profiles/r02_diag_bwd*.log).  Mixed f16 / bf16 operands in one MMA trap, so V (never an MMA operand) stays
+// bf16.  TTT_B200_OPERANDS=bf16 selects the bf16 instantiation (A/B runs).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -66,31 +74,6 @@ __device__ __forceinline__ float gelu_only(float z) {
   return fmaf(hz, t, hz);
 }
 
-// ---- packed-half GELU (2 elements per instruction on the FMA pipe, one MUFU.TANH per pair).  The result is converted
-// to bf16 for the X2 tile: a kind::f16 MMA with A = f16 and B = bf16 traps (illegal instruction) on sm_100a, measured
-// with umma self-test mode 4, so all MMA operands stay bf16.
-__device__ __forceinline__ __half2 h2_tanh(__half2 x) {
-  uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
-  return *reinterpret_cast<__half2*>(&yi);
-}
-__device__ __forceinline__ uint32_t h2_bits(__half2 x) { return *reinterpret_cast<uint32_t*>(&x); }
-__device__ __forceinline__ uint32_t gelu_h2(float z0, float z1, __half2 b1h, uint32_t* grad_bits) {
-  const __half2 c0 = __float2half2_rn(0.79788456f), c1 = __float2half2_rn(0.79788456f * 0.044715f);
-  const __half2 c3 = __float2half2_rn(3.0f * 0.79788456f * 0.044715f), hh = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
-  const __half2 z = __hadd2(__floats2half2_rn(z0, z1), b1h);
-  const __half2 z2 = __hmul2(z, z);
-  const __half2 t = h2_tanh(__hmul2(z, __hfma2(c1, z2, c0)));
-  const __half2 hz = __hmul2(z, hh);
-  if (grad_bits) {
-    const __half2 s = __hfma2(__hneg2(t), t, one);
-    const __half2 g = __hfma2(__hmul2(hz, s), __hfma2(c3, z2, c0), __hfma2(hh, t, hh));
-    *grad_bits = h2_bits(g);
-  }
-  const __half2 x = __hfma2(hz, t, hz);
-  return pack_bf16(__low2float(x), __high2float(x));
-}
-
 struct FwdParams {
   const __nv_bfloat16* last_eta;  // [B,H,NC,64]
   const float* ln_w;              // [H,64]
@@ -100,12 +83,6 @@ struct FwdParams {
   float *W1o, *b1o, *W2o, *b2o;        // final state (may be null)
   __nv_bfloat16* Out;                  // [B,H,NC,64,64]
   int B, H, NC, ckpt_group, K;
-  // trajectory mode (backward pass, csrc/ttt_mlp_bwd.cu): run steps [t0, t0+nsteps) from the state stored at
-  // W1[(bh*init_stride + init_off)] and save, for s = 0..nsteps, the bf16 operand images of the state entering step
-  // t0+s: img[(bh*(G+1)+s)] = { W1^T image 32 KB, W2 image 32 KB } in smem-tile byte order, b1img, b2img (fp32).
-  int t0, nsteps, init_stride, init_off, img_slots;
-  uint8_t* img;
-  float *b1img, *b2img;
   unsigned* dbg;  // phase-timing buffer (debug builds)
 };
 
@@ -121,22 +98,31 @@ __device__ __forceinline__ void store_w2_row(float* W2g, int j, const uint32_t* 
     dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                          __uint_as_float(v[4 * i + 3]));
 }
-// 32 fp32 (registers) -> bf16 -> 4 chunks of a SW128 row
-__device__ __forceinline__ void store_row_bf16(uint32_t tile_saddr, int row, int chunk0, const uint32_t* v,
-                                               uint8_t* gmirror = nullptr) {
+// 32 fp32 (registers) -> operand format -> 4 chunks of a SW128 row
+template <bool kF16>
+__device__ __forceinline__ void store_row_op(uint32_t tile_saddr, int row, int chunk0, const uint32_t* v) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t p0 = pack_bf16(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
-    uint32_t p1 = pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
-    uint32_t p2 = pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
-    uint32_t p3 = pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
-    const uint32_t off = sw128_off(row, chunk0 + c);
-    st_shared_v4(tile_saddr + off, p0, p1, p2, p3);
-    if (gmirror) *reinterpret_cast<uint4*>(gmirror + off) = make_uint4(p0, p1, p2, p3);
+    uint32_t p0 = pack_op<kF16>(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
+    uint32_t p1 = pack_op<kF16>(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+    uint32_t p2 = pack_op<kF16>(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+    uint32_t p3 = pack_op<kF16>(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+    st_shared_v4(tile_saddr + sw128_off(row, chunk0 + c), p0, p1, p2, p3);
+  }
+}
+// in-place bf16 -> fp16 conversion of one [64][64] token tile (8 KB = 512 chunks of 16 bytes; 2 per thread; element-wise,
+// so the swizzle does not matter)
+__device__ __forceinline__ void tile_bf16_to_f16(uint32_t tile_saddr, int tid) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t a = tile_saddr + (uint32_t)(tid + 256 * i) * 16u;
+    uint32_t w0, w1, w2, w3;
+    ld_shared_v4(a, w0, w1, w2, w3);
+    st_shared_v4(a, bf16x2_to_f16x2(w0), bf16x2_to_f16x2(w1), bf16x2_to_f16x2(w2), bf16x2_to_f16x2(w3));
   }
 }
 
-template <bool kTraj, bool kHalf>
+template <bool kF16>
 __global__ void __launch_bounds__(NT, 1)
 ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -146,7 +132,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp_u = uniform_warp_id();  // == warp, provably warp-uniform: single-thread issue blocks branch on it
   const int bh = blockIdx.x;
   const int head = bh % p.H;
-  const int NC = kTraj ? p.nsteps : p.NC;  // number of steps this launch runs
+  const int NC = p.NC;
 
   float* b2s = reinterpret_cast<float*>(smem + SM_MISC);
   float* lnw = b2s + 64;
@@ -172,7 +158,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (tid < 64) {
     lnw[tid] = p.ln_w[head * 64 + tid];
     lnb[tid] = p.ln_b[head * 64 + tid];
-    b2s[tid] = p.b2[((size_t)bh * p.init_stride + p.init_off) * 64 + tid];
+    b2s[tid] = p.b2[(size_t)bh * 64 + tid];
     db2acc[tid] = 0.f;
   }
   tc_fence_before();
@@ -182,9 +168,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int half = warp >> 2;                                    // which 128-row half of the hidden dim
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;  // this warp's TMEM lane quarter
   const int j = tid;                                             // hidden unit owned by this thread (P2/P6/P8)
-  const size_t row_base = ((size_t)bh * p.NC + (kTraj ? p.t0 : 0)) * CS;  // first token row handled, in [B*H*NC*CS, 64]
-  const size_t st_idx = (size_t)bh * p.init_stride + p.init_off;            // which stored state to start from
-  uint8_t* img0 = kTraj ? p.img + (size_t)bh * p.img_slots * 65536 : nullptr;
+  const size_t row_base = (size_t)bh * p.NC * CS;                // first token row of this sequence, in [B*H*NC*CS, 64]
 
   // prologue TMA: K_0, V_0 into slot 0
   if (warp_u == 0 && (NC > 0) && elect_one()) {
@@ -193,46 +177,45 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_2d(smem + SM_V, &tmV, 0, (int)row_base, &tma_bar[0]);
   }
 
-  // ---- initial state: global fp32 -> TMEM accumulators + bf16 operand copies (+ checkpoint 0)
-  float b1r = p.b1[st_idx * HID + j];
+  // ---- initial state: global fp32 -> TMEM accumulators + operand copies (+ checkpoint 0)
+  float b1r = p.b1[(size_t)bh * HID + j];
   {
-    const float* W1g = p.W1 + st_idx * F * HID;
-    const float* W2g = p.W2 + st_idx * HID * F;
+    const float* W1g = p.W1 + (size_t)bh * F * HID;
+    const float* W2g = p.W2 + (size_t)bh * HID * F;
     uint32_t v[32];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(W1g[(size_t)(32 * c + i) * HID + j]);
       tmem_st32(tmem + lane_addr + TM_W1 + 64 * half + 32 * c, v);
-      store_row_bf16(sbase + SM_W1B, j, 4 * c, v, img0);
-      if (!kTraj && p.W1c) store_w1_col(p.W1c + ((size_t)bh * p.K) * F * HID, j, v, 32 * c);
+      store_row_op<kF16>(sbase + SM_W1B, j, 4 * c, v);
+      if (p.W1c) store_w1_col(p.W1c + ((size_t)bh * p.K) * F * HID, j, v, 32 * c);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(W2g[(size_t)j * F + 32 * c + i]);
       tmem_st32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
-      store_row_bf16(sbase + SM_W2B, j, 4 * c, v, img0 ? img0 + 32768 : nullptr);
-      if (!kTraj && p.W2c) store_w2_row(p.W2c + ((size_t)bh * p.K) * HID * F, j, v, 32 * c);
+      store_row_op<kF16>(sbase + SM_W2B, j, 4 * c, v);
+      if (p.W2c) store_w2_row(p.W2c + ((size_t)bh * p.K) * HID * F, j, v, 32 * c);
     }
-    if (!kTraj && p.b1c) p.b1c[((size_t)bh * p.K) * HID + j] = b1r;
-    if (!kTraj && p.b2c && tid < 64) p.b2c[((size_t)bh * p.K) * F + tid] = p.b2[st_idx * 64 + tid];
-    if (kTraj) {
-      p.b1img[((size_t)bh * p.img_slots) * HID + j] = b1r;
-      if (tid < 64) p.b2img[((size_t)bh * p.img_slots) * F + tid] = p.b2[st_idx * 64 + tid];
-    }
+    if (p.b1c) p.b1c[((size_t)bh * p.K) * HID + j] = b1r;
+    if (p.b2c && tid < 64) p.b2c[((size_t)bh * p.K) * F + tid] = p.b2[(size_t)bh * 64 + tid];
     tc_wait_st();
+  }
+  if (kF16 && NC > 0) {  // K_0 has landed long ago (the state staging above took microseconds): bf16 -> f16 in place
+    mbar_wait(&tma_bar[0], 0);
+    tile_bf16_to_f16(sbase + SM_KQ, tid);
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
 
-  constexpr uint32_t IDESC_A = make_idesc_bf16(128, 128, false, false);  // D1: A K-major, B K-major
-  constexpr uint32_t IDESC_A64 = make_idesc_bf16(128, 64, false, false);  // trajectory mode: K side only
-  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true);  // D2: A (X2) MN-major, B MN-major
-  constexpr uint32_t IDESC_U2 = make_idesc_bf16(128, 64, false, true);  // W2 update: A = X2^T
-  constexpr uint32_t IDESC_C = make_idesc_bf16(128, 64, false, false);   // D3
-  constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true);    // state updates: A K-major, B MN-major
+  constexpr uint32_t IDESC_A = make_idesc_bf16(128, 128, false, false, false, kF16, kF16);  // D1: A K-major, B K-major
+  constexpr uint32_t IDESC_B = make_idesc_bf16(128, 64, true, true, false, kF16, kF16);     // D2: A (X2) MN-major, B MN-major
+  constexpr uint32_t IDESC_U2 = make_idesc_bf16(128, 64, false, true, false, kF16, kF16);   // W2 update: A = X2^T
+  constexpr uint32_t IDESC_C = make_idesc_bf16(128, 64, false, false, false, kF16, kF16);   // D3
+  constexpr uint32_t IDESC_U = make_idesc_bf16(128, 64, false, true, false, kF16, kF16);    // state updates: A K-major, B MN-major
 
   uint32_t mma_phase = 0;
-  auto issue_p1 = [&](int it_next) {  // thread 0 only: wait for the tiles of iteration it_next, then D1 = W1b^T . [K|Q]^T
+  auto issue_p1 = [&](int it_next) {  // one thread: wait for the tiles of iteration it_next, then D1 = W1b^T . [K|Q]^T
     const int sl = it_next & 1;
     mbar_wait(&tma_bar[sl], (it_next >> 1) & 1);
     tc_fence_after();
@@ -242,7 +225,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint64_t db = make_desc_sw128(sbase + SM_KQ + sl * 16384, 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), kTraj ? IDESC_A64 : IDESC_A, k > 0);
+        umma_ss(tmem + TM_D1 + 128 * h, desc_advance(da, 32 * k), desc_advance(db, 32 * k), IDESC_A, k > 0);
     }
     tc_commit(mma_bar);
   };
@@ -250,13 +233,12 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   TICK_DECL(12, 224)
   uint32_t gp[32];  // gelu'(Z1) for this thread's hidden unit, 64 tokens, packed bf16x2
 
-  for (int it = 0; it < (kTraj ? NC : NC + 1); ++it) {
+  for (int it = 0; it < NC + 1; ++it) {
     const int slot = it & 1;
-    const bool has_k = it < NC, has_q = !kTraj && it > 0;
+    const bool has_k = it < NC, has_q = it > 0;
     const uint32_t kq = sbase + SM_KQ + slot * 16384;
     const uint32_t vt = sbase + SM_V + slot * 8192;
 
-    // prefetch eta for the LN threads of the K side
     // eta of this step for the K-side LN rows: fetched as raw bf16 bits here, converted at the point of use (P4) so the
     // global-load latency hides behind P1-P3 instead of stalling the warp at the top of the iteration
     unsigned short eta_raw = 0;
@@ -266,15 +248,15 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     TICK(0);
     mbar_wait(&tma_bar[slot], (it >> 1) & 1);
     TICK(1);
-    if (warp_u == 0 && ((kTraj ? (it + 1 < NC) : (it < NC))) && elect_one()) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
+    if (warp_u == 0 && (it < NC) && elect_one()) {  // next iteration's tiles: K_{it+1}, V_{it+1} (if any) and Q_{it}
       const int ns = slot ^ 1;
       const bool nk = (it + 1) < NC;
-      mbar_expect_tx(&tma_bar[ns], (nk ? 16384 : 0) + (kTraj ? 0 : 8192));
+      mbar_expect_tx(&tma_bar[ns], (nk ? 16384 : 0) + 8192);
       if (nk) {
         tma_load_2d(smem + SM_KQ + ns * 16384, &tmK, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
         tma_load_2d(smem + SM_V + ns * 8192, &tmV, 0, (int)(row_base + (size_t)(it + 1) * CS), &tma_bar[ns]);
       }
-      if (!kTraj) tma_load_2d(smem + SM_KQ + ns * 16384 + 8192, &tmQ, 0, (int)(row_base + (size_t)it * CS), &tma_bar[ns]);
+      tma_load_2d(smem + SM_KQ + ns * 16384 + 8192, &tmQ, 0, (int)(row_base + (size_t)it * CS), &tma_bar[ns]);
     }
 
     // ---------------- P1: D1[h] = W1b^T[h] . [K | Q]^T  (M=128, N=128, K=64) -- issued early, at the end of the
@@ -284,7 +266,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     TICK(2);
 
-    // ---------------- P2: gelu on D1 row j -> X2^T / X2bar^T (bf16, SW128 rows); keep gelu'(Z1)
+    // ---------------- P2: gelu on D1 row j -> X2^T / X2bar^T (operand format, SW128 rows); keep gelu'(Z1)
     {
       const uint32_t tsrc = tmem + lane_addr + TM_D1 + 128 * half;
 #pragma unroll
@@ -293,32 +275,21 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t v[32];
         tmem_ld32(tsrc + 32 * c, v);
         tc_wait_ld();
-        if (kHalf) {
-          const __half2 b1h = __float2half2_rn(b1r);
-          uint32_t o[16];
+        if (c < 2) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            o[i / 2] = gelu_h2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), b1h, c < 2 ? &gp[16 * c + i / 2] : nullptr);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            st_shared_v4(sbase + SM_X2 + (c >> 1) * 32768 + sw128_off(j, 4 * (c & 1) + q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        } else {
-          if (c < 2) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float g0, g1;
-              float x0 = gelu_and_grad(__uint_as_float(v[i]) + b1r, g0);
-              float x1 = gelu_and_grad(__uint_as_float(v[i + 1]) + b1r, g1);
-              v[i] = __float_as_uint(x0);
-              v[i + 1] = __float_as_uint(x1);
-              gp[16 * c + i / 2] = pack_bf16(g0, g1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_only(__uint_as_float(v[i]) + b1r));
+          for (int i = 0; i < 32; i += 2) {
+            float g0, g1;
+            float x0 = gelu_and_grad(__uint_as_float(v[i]) + b1r, g0);
+            float x1 = gelu_and_grad(__uint_as_float(v[i + 1]) + b1r, g1);
+            v[i] = __float_as_uint(x0);
+            v[i + 1] = __float_as_uint(x1);
+            gp[16 * c + i / 2] = pack_bf16(g0, g1);
           }
-          store_row_bf16(sbase + SM_X2 + (c >> 1) * 32768, j, 4 * (c & 1), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_only(__uint_as_float(v[i]) + b1r));
         }
+        store_row_op<kF16>(sbase + SM_X2 + (c >> 1) * 32768, j, 4 * (c & 1), v);
       }
     }
     fence_proxy_async();
@@ -367,7 +338,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 0; i < 32; ++i) z[i] = (z[i] - mu) * rstd;  // x_hat
       }
       if (kside) {
-        // grad_out = gamma*xhat + beta - (V - K); gxh = grad_out*gamma
+        // grad_out = gamma*xhat + beta - (V - K); gxh = grad_out*gamma        (K tile in operand format, V tile bf16)
         float g[32];
         float s1 = 0.f, s2 = 0.f;
         if (active) {
@@ -379,8 +350,8 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = 8 * c + 2 * e, f = 32 * ch + i;
-              const float t0 = bf16_lo(vv[e]) - bf16_lo(kk[e]);
-              const float t1 = bf16_hi(vv[e]) - bf16_hi(kk[e]);
+              const float t0 = bf16_lo(vv[e]) - op_lo<kF16>(kk[e]);
+              const float t1 = bf16_hi(vv[e]) - op_hi<kF16>(kk[e]);
               g[i] = (fmaf(lnw[f], z[i], lnb[f]) - t0) * lnw[f];
               g[i + 1] = (fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]) - t1) * lnw[f + 1];
               s1 += g[i] + g[i + 1];
@@ -401,10 +372,11 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < 32; ++i) g[i] = (fmaf(64.0f, g[i], -s1) - z[i] * s2) * sc;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            st_shared_v4(sbase + SM_G2 + sw128_off(row, 4 * ch + c), pack_bf16(g[8 * c], g[8 * c + 1]),
-                         pack_bf16(g[8 * c + 2], g[8 * c + 3]), pack_bf16(g[8 * c + 4], g[8 * c + 5]),
-                         pack_bf16(g[8 * c + 6], g[8 * c + 7]));
-          // b2 update = column sums of G2 over the 64 token rows (butterfly over the warp, then shared atomics)
+            st_shared_v4(sbase + SM_G2 + sw128_off(row, 4 * ch + c), pack_op<kF16>(g[8 * c], g[8 * c + 1]),
+                         pack_op<kF16>(g[8 * c + 2], g[8 * c + 3]), pack_op<kF16>(g[8 * c + 4], g[8 * c + 5]),
+                         pack_op<kF16>(g[8 * c + 6], g[8 * c + 7]));
+          // b2 update = column sums of G2 over the 64 token rows (butterfly over the warp, then one shared add per row half:
+          // db2acc starts at zero every step and takes exactly two addends, so the sum does not depend on their order)
 #pragma unroll
           for (int m = 16; m >= 1; m >>= 1) {
             const bool up = (lane & m) != 0;
@@ -429,8 +401,8 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = 8 * c + 2 * e, f = 32 * ch + i;
-              const float o0 = bf16_lo(qq[e]) + fmaf(lnw[f], z[i], lnb[f]);
-              const float o1 = bf16_hi(qq[e]) + fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]);
+              const float o0 = op_lo<kF16>(qq[e]) + fmaf(lnw[f], z[i], lnb[f]);
+              const float o1 = op_hi<kF16>(qq[e]) + fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]);
               o[e] = pack_bf16(o0, o1);
             }
             *reinterpret_cast<uint4*>(og + 8 * c) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -470,7 +442,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     TICK(6);
 
-    // ---------------- P6: G1^T row j = D3 row j * gelu'(Z1) (bf16) ; b1 += sum ; threads 0-63: b2 += column sums of G2
+    // ---------------- P6: G1^T row j = D3 row j * gelu'(Z1) ; b1 += sum ; threads 0-63: b2 += column sums of G2
     {
       const uint32_t tsrc = tmem + lane_addr + TM_D3 + 128 * half;
       float acc = 0.f;
@@ -482,13 +454,13 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const uint32_t gpk = gp[16 * c + i / 2];
-          float a0 = __uint_as_float(v[i]) * (kHalf ? __low2float(*reinterpret_cast<const __half2*>(&gpk)) : bf16_lo(gpk));
-          float a1 = __uint_as_float(v[i + 1]) * (kHalf ? __high2float(*reinterpret_cast<const __half2*>(&gpk)) : bf16_hi(gpk));
+          float a0 = __uint_as_float(v[i]) * bf16_lo(gpk);
+          float a1 = __uint_as_float(v[i + 1]) * bf16_hi(gpk);
           acc += a0 + a1;
           v[i] = __float_as_uint(a0);
           v[i + 1] = __float_as_uint(a1);
         }
-        store_row_bf16(sbase + SM_X2 + 32768, j, 4 * c, v);
+        store_row_op<kF16>(sbase + SM_X2 + 32768, j, 4 * c, v);
       }
       b1r += acc;
       if (tid < 64) {  // fold the column sums of G2 gathered in P4 into b2
@@ -519,43 +491,44 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     TICK(8);
 
-    // ---------------- P8: re-materialise bf16 operand copies of the new state (+ checkpoint / final state)
+    // ---------------- P8: re-materialise the operand copies of the new state (+ checkpoint / final state)
     {
       const int nstep = it + 1;  // state now equals the state entering mini-batch nstep
-      const bool ck = !kTraj && (p.W1c != nullptr) && (nstep < NC) && (nstep % p.ckpt_group == 0);
-      const bool fin = !kTraj && (p.W1o != nullptr) && (nstep == NC);
-      uint8_t* imgs = kTraj ? img0 + (size_t)nstep * 65536 : nullptr;
+      const bool ck = (p.W1c != nullptr) && (nstep < NC) && (nstep % p.ckpt_group == 0);
+      const bool fin = (p.W1o != nullptr) && (nstep == NC);
       const size_t kidx = ck ? ((size_t)bh * p.K + nstep / p.ckpt_group) : 0;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + TM_W1 + 64 * half + 32 * c, v);
         tc_wait_ld();
-        store_row_bf16(sbase + SM_W1B, j, 4 * c, v, imgs);
+        store_row_op<kF16>(sbase + SM_W1B, j, 4 * c, v);
         if (ck) store_w1_col(p.W1c + kidx * F * HID, j, v, 32 * c);
         if (fin) store_w1_col(p.W1o + (size_t)bh * F * HID, j, v, 32 * c);
+      }
+      if (kF16) {  // next iteration's token tiles (TMA issued at the top of this iteration): bf16 -> f16 in place
+        const int ns = slot ^ 1;
+        mbar_wait(&tma_bar[ns], ((it + 1) >> 1) & 1);
+        if (nstep < NC) tile_bf16_to_f16(sbase + SM_KQ + ns * 16384, tid);  // K_{it+1}
+        tile_bf16_to_f16(sbase + SM_KQ + ns * 16384 + 8192, tid);            // Q_{it}
       }
       // W1b is complete: start the next iteration's D1 now, it runs under the W2 conversion below
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (warp_u == 0 && ((kTraj ? (it + 1 < NC) : true)) && elect_one()) issue_p1(it + 1);
+      if (warp_u == 0 && elect_one()) issue_p1(it + 1);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + TM_W2 + 64 * half + 32 * c, v);
         tc_wait_ld();
-        store_row_bf16(sbase + SM_W2B, j, 4 * c, v, imgs ? imgs + 32768 : nullptr);
+        store_row_op<kF16>(sbase + SM_W2B, j, 4 * c, v);
         if (ck) store_w2_row(p.W2c + kidx * HID * F, j, v, 32 * c);
         if (fin) store_w2_row(p.W2o + (size_t)bh * HID * F, j, v, 32 * c);
       }
       if (ck) {
         p.b1c[kidx * HID + j] = b1r;
         if (tid < 64) p.b2c[kidx * F + tid] = b2s[tid];  // b2s was updated by the same thread in P6
-      }
-      if (kTraj) {
-        p.b1img[((size_t)bh * p.img_slots + nstep) * HID + j] = b1r;
-        if (tid < 64) p.b2img[((size_t)bh * p.img_slots + nstep) * F + tid] = b2s[tid];
       }
       if (fin) {
         p.b1o[(size_t)bh * HID + j] = b1r;
@@ -575,43 +548,15 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int g_half_gelu = -1;  // -1: read TTT_B200_HALF_GELU from the environment once
-static bool use_half_gelu() {
-  if (g_half_gelu < 0) {
-    const char* e = getenv("TTT_B200_HALF_GELU");
-    g_half_gelu = (e && e[0] == '1') ? 1 : 0;
+static int g_bf16_operands = -1;  // -1: read TTT_B200_OPERANDS from the environment once ("bf16" selects the A/B variant)
+static bool use_bf16_operands() {
+  if (g_bf16_operands < 0) {
+    const char* e = getenv("TTT_B200_OPERANDS");
+    g_bf16_operands = (e && e[0] == 'b') ? 1 : 0;
   }
-  return g_half_gelu != 0;
+  return g_bf16_operands != 0;
 }
-void set_half_gelu(int on) { g_half_gelu = on ? 1 : 0; }
-
-static cudaError_t launch_common(bool traj, const void* XQ, const void* XK, const void* XV, FwdParams& p, cudaStream_t stream) {
-  CUtensorMap tq, tk, tv;
-  const uint64_t rows = (uint64_t)p.B * p.H * p.NC * CS;
-  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-  if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
-    return cudaErrorInvalidValue;
-  g_where = "forward/trajectory launch";
-  static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
-  bool& attr_done = *device_once(attr_done_dev);
-  if (!attr_done) {
-    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
-    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
-    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
-    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
-    attr_done = true;
-  }
-  p.dbg = traj ? nullptr : g_timing_buf;
-  const bool hg = use_half_gelu();
-  if (traj) {
-    if (hg) ttt_mlp_fwd_kernel<true, true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
-    else    ttt_mlp_fwd_kernel<true, false><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
-  } else {
-    if (hg) ttt_mlp_fwd_kernel<false, true><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
-    else    ttt_mlp_fwd_kernel<false, false><<<p.B * p.H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
-  }
-  return cudaGetLastError();
-}
+bool mlp_operands_bf16() { return use_bf16_operands(); }
 
 cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                const float* ln_b, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -627,24 +572,23 @@ cudaError_t launch_mlp_forward(const void* XQ, const void* XK, const void* XV, c
   p.Out = reinterpret_cast<__nv_bfloat16*>(Out);
   p.B = B; p.H = H; p.NC = NC; p.ckpt_group = ckpt_group;
   p.K = (NC + ckpt_group - 1) / ckpt_group;
-  p.t0 = 0; p.nsteps = NC; p.init_stride = 1; p.init_off = 0; p.img_slots = 0;
-  return launch_common(false, XQ, XK, XV, p, stream);
-}
-
-// Trajectory pass of the backward: recompute steps [t0, t0+nsteps) of every sequence from checkpoint `k` and save the
-// bf16 operand images of the nsteps+1 states (see FwdParams).  Checkpoint tensors are [B,H,K,...].
-cudaError_t launch_mlp_trajectory(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
-                                  const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
-                                  const float* b2c, int B, int H, int NC, int K, int k, int t0, int nsteps,
-                                  uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream) {
-  FwdParams p{};
-  p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
-  p.ln_w = ln_w; p.ln_b = ln_b;
-  p.W1 = W1c; p.b1 = b1c; p.W2 = W2c; p.b2 = b2c;
-  p.B = B; p.H = H; p.NC = NC; p.ckpt_group = 1; p.K = K;
-  p.t0 = t0; p.nsteps = nsteps; p.init_stride = K; p.init_off = k; p.img_slots = img_slots;
-  p.img = img; p.b1img = b1img; p.b2img = b2img;
-  return launch_common(true, XK, XK, XV, p, stream);
+  CUtensorMap tq, tk, tv;
+  const uint64_t rows = (uint64_t)B * H * NC * CS;
+  if (rows > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+  if (make_token_tmap(&tq, XQ, rows) || make_token_tmap(&tk, XK, rows) || make_token_tmap(&tv, XV, rows))
+    return cudaErrorInvalidValue;
+  g_where = "forward launch";
+  static bool attr_done_dev[64] = {};  // function attributes are per device
+  bool& attr_done = *device_once(attr_done_dev);
+  if (!attr_done) {
+    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
+    TB_TRY(cudaFuncSetAttribute(ttt_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL), "smem attr");
+    attr_done = true;
+  }
+  p.dbg = g_timing_buf;
+  if (use_bf16_operands()) ttt_mlp_fwd_kernel<false><<<B * H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  else                     ttt_mlp_fwd_kernel<true><<<B * H, NT, SM_TOTAL, stream>>>(tq, tk, tv, p);
+  return cudaGetLastError();
 }
 
 }  // namespace tb

@@ -10,6 +10,11 @@
 // forward kernel in trajectory mode has a 48 KB loop.  Here every per-thread element loop is a rolled loop over
 // 16-column chunks (values that the forward keeps in registers across phases live in shared memory instead), which
 // keeps the whole step loop inside L1.5.  This kernel has 2x slack against the K-side kernel, so the lost ILP is free.
+//
+// Operand format: as in the forward (template kF16, see ttt_mlp_fwd.cu) the MMA operand tiles of THIS kernel are fp16, so
+// that the recomputed trajectory follows the forward's; the state images it exports for the K-side / Q-side kernels are
+// bf16 (those kernels mix them with gradient operands, which need bf16's range), written by the owning threads straight
+// to global memory in the image's tile byte order.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -26,6 +31,42 @@ using bwd::gelu1;
 using bwd::ld_row16;
 using bwd::st_row16;
 using bwd::warp_colsum16;
+
+// operand-format variants of bwd_common.cuh's row helpers
+template <bool kF16>
+__device__ __forceinline__ void ld_row16_op(uint32_t tile, int row, int chunk0, float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t a, b, cc, d;
+    ld_shared_v4(tile + sw128_off(row, chunk0 + c), a, b, cc, d);
+    v[8 * c + 0] = op_lo<kF16>(a); v[8 * c + 1] = op_hi<kF16>(a); v[8 * c + 2] = op_lo<kF16>(b); v[8 * c + 3] = op_hi<kF16>(b);
+    v[8 * c + 4] = op_lo<kF16>(cc); v[8 * c + 5] = op_hi<kF16>(cc); v[8 * c + 6] = op_lo<kF16>(d); v[8 * c + 7] = op_hi<kF16>(d);
+  }
+}
+template <bool kF16>
+__device__ __forceinline__ void st_row16_op(uint32_t tile, int row, int chunk0, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    st_shared_v4(tile + sw128_off(row, chunk0 + c), pack_op<kF16>(v[8 * c], v[8 * c + 1]), pack_op<kF16>(v[8 * c + 2], v[8 * c + 3]),
+                 pack_op<kF16>(v[8 * c + 4], v[8 * c + 5]), pack_op<kF16>(v[8 * c + 6], v[8 * c + 7]));
+}
+// 16 fp32 of row `row` -> bf16 -> the two 16-byte chunks chunk0, chunk0+1 of a [256][64] image block in global memory
+__device__ __forceinline__ void st_image16(uint8_t* img_block, int row, int chunk0, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    *reinterpret_cast<uint4*>(img_block + sw128_off(row, chunk0 + c)) =
+        make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]), pack_bf16(v[8 * c + 4], v[8 * c + 5]),
+                   pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+__device__ __forceinline__ void tile_bf16_to_f16(uint32_t tile_saddr, int tid) {  // [64][64] tile, in place
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t a = tile_saddr + (uint32_t)(tid + 256 * i) * 16u;
+    uint32_t w0, w1, w2, w3;
+    ld_shared_v4(a, w0, w1, w2, w3);
+    st_shared_v4(a, bf16x2_to_f16x2(w0), bf16x2_to_f16x2(w1), bf16x2_to_f16x2(w2), bf16x2_to_f16x2(w3));
+  }
+}
 
 constexpr int CS = 64, F = 64, HID = 256, NT = 256;
 
@@ -53,6 +94,7 @@ struct TrajParams {
   float *b1img, *b2img;                 // [BH][img_slots][256], [BH][img_slots][64]
 };
 
+template <bool kF16>
 __global__ void __launch_bounds__(NT, 1)
 ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const TrajParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -122,23 +164,29 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = W1g[(size_t)(16 * c + i) * HID + j];
       tmem_st16(tmem + lane_addr + TM_W1 + 64 * half + 16 * c, reinterpret_cast<uint32_t*>(v));
-      st_row16(sbase + SM_W1B, j, 2 * c, v);
+      st_row16_op<kF16>(sbase + SM_W1B, j, 2 * c, v);
+      st_image16(img, j, 2 * c, v);  // image of the state entering step t0 (slot 0)
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = W2g[(size_t)j * F + 16 * c + i];
       tmem_st16(tmem + lane_addr + TM_W2 + 64 * half + 16 * c, reinterpret_cast<uint32_t*>(v));
-      st_row16(sbase + SM_W2B, j, 2 * c, v);
+      st_row16_op<kF16>(sbase + SM_W2B, j, 2 * c, v);
+      st_image16(img + 32768, j, 2 * c, v);
     }
     b1img[j] = b1r;
     if (tid < 64) b2img[tid] = b2s[tid];
     tc_wait_st();
   }
+  if (kF16) {  // K_0 landed during the state staging: bf16 -> f16 in place (V is not an MMA operand and stays bf16)
+    mbar_wait(&tma_bar[0], 0);
+    tile_bf16_to_f16(sbase + SM_K, tid);
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
 
-  constexpr uint32_t IDESC_KK = make_idesc_bf16(128, 64, false, false);  // A K-major, B K-major
-  constexpr uint32_t IDESC_NN = make_idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major
-  constexpr uint32_t IDESC_KN = make_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
+  constexpr uint32_t IDESC_KK = make_idesc_bf16(128, 64, false, false, false, kF16, kF16);  // A K-major, B K-major
+  constexpr uint32_t IDESC_NN = make_idesc_bf16(128, 64, true, true, false, kF16, kF16);    // A MN-major, B MN-major
+  constexpr uint32_t IDESC_KN = make_idesc_bf16(128, 64, false, true, false, kF16, kF16);   // A K-major, B MN-major
   uint32_t mma_phase = 0;
 
   // D1[h] = W1b^T[h] . K^T  (M = 128 hidden, N = 64 tokens, K = 64)
@@ -155,12 +203,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
     tc_commit(mma_bar);
   };
-  if (warp_u == 0 && elect_one()) {
-    bulk_store_1d(img, smem + SM_W1B, 32768);  // image of the state entering step t0 (slot 0)
-    bulk_store_1d(img + 32768, smem + SM_W2B, 32768);
-    bulk_commit();
-    issue_p1(0);
-  }
+  if (warp_u == 0 && elect_one()) issue_p1(0);
 
 #pragma unroll 1
   for (int it = 0; it < n; ++it) {
@@ -191,8 +234,8 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = gelu1(v[i] + b1r, g[i]);
-      st_row16(sbase + SM_X2, j, 2 * c, v);
-      st_row16(sbase + SM_GP, j, 2 * c, g);
+      st_row16_op<kF16>(sbase + SM_X2, j, 2 * c, v);
+      st_row16(sbase + SM_GP, j, 2 * c, g);  // gelu' is not an operand (bf16); overwritten by G1^T in P6
     }
     fence_proxy_async();
     tc_fence_before();
@@ -235,7 +278,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       for (int c = 0; c < 2; ++c) {
         float z[16], kk[16], vv[16];
         tmem_ld16(tmem + lane_addr + TM_D2 + 32 * ch + 16 * c, reinterpret_cast<uint32_t*>(z));
-        ld_row16(kt, r, 4 * ch + 2 * c, kk);
+        ld_row16_op<kF16>(kt, r, 4 * ch + 2 * c, kk);
         ld_row16(vt, r, 4 * ch + 2 * c, vv);
         tc_wait_ld();
 #pragma unroll
@@ -258,7 +301,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       for (int c = 0; c < 2; ++c) {
         float z[16], kk[16], vv[16];
         tmem_ld16(tmem + lane_addr + TM_D2 + 32 * ch + 16 * c, reinterpret_cast<uint32_t*>(z));
-        ld_row16(kt, r, 4 * ch + 2 * c, kk);
+        ld_row16_op<kF16>(kt, r, 4 * ch + 2 * c, kk);
         ld_row16(vt, r, 4 * ch + 2 * c, vv);
         tc_wait_ld();
 #pragma unroll
@@ -268,7 +311,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           const float g = (fmaf(lnw[f], xh, lnb[f]) - (vv[i] - kk[i])) * lnw[f];
           z[i] = (fmaf(64.0f, g, -s1) - xh * s2) * sc;  // G2 = -eta * gradZ2
         }
-        st_row16(sbase + SM_G2, r, 4 * ch + 2 * c, z);
+        st_row16_op<kF16>(sbase + SM_G2, r, 4 * ch + 2 * c, z);
         warp_colsum16(z, lane);  // b2 update = column sums of G2 over the token rows
         if ((lane & 1) == 0) atomicAdd(&db2acc[32 * ch + 16 * c + (lane >> 1)], z[0]);
       }
@@ -311,7 +354,7 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) { v[i] *= g[i]; acc += v[i]; }
-        st_row16(sbase + SM_GP, j, 2 * c, v);
+        st_row16_op<kF16>(sbase + SM_GP, j, 2 * c, v);
       }
       b1r += acc;
       if (tid < 64) {
@@ -325,7 +368,6 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
     // ---- P7: W1^T[h] += G1^T[h] . K
     if (warp_u == 0 && elect_one()) {
-      bulk_wait_read<0>();  // the previous image store has read SM_W1B / SM_W2B (rewritten in P8, after this commit)
       tc_fence_after();
       const uint64_t db = make_desc_sw128(kt, 1024, 1024);
 #pragma unroll 1
@@ -340,28 +382,32 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     mma_phase ^= 1;
     tc_fence_after();
 
-    // ---- P8: bf16 operand copies of the new state = image slot it + 1
+    // ---- P8: operand copies of the new state (smem) + its bf16 image (global) = image slot it + 1
+    const bool store_img = store_last || it + 1 < n;
+    uint8_t* img_n = img + (size_t)(it + 1) * 65536;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       float v[16];
       tmem_ld16(tmem + lane_addr + TM_W1 + 64 * half + 16 * c, reinterpret_cast<uint32_t*>(v));
       tc_wait_ld();
-      st_row16(sbase + SM_W1B, j, 2 * c, v);
+      st_row16_op<kF16>(sbase + SM_W1B, j, 2 * c, v);
+      if (store_img) st_image16(img_n, j, 2 * c, v);
+    }
+    if (kF16 && it + 1 < n) {  // next step's K tile (TMA issued at the top of this step): bf16 -> f16 in place
+      mbar_wait(&tma_bar[slot ^ 1], ((it + 1) >> 1) & 1);
+      tile_bf16_to_f16(sbase + SM_K + (slot ^ 1) * 8192, tid);
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    const bool store_img = store_last || it + 1 < n;
-    if (warp_u == 0 && elect_one()) {
-      if (store_img) bulk_store_1d(img + (size_t)(it + 1) * 65536, smem + SM_W1B, 32768);
-      if (it + 1 < n) issue_p1(it + 1);  // runs under the W2 conversion below
-    }
+    if (warp_u == 0 && (it + 1 < n) && elect_one()) issue_p1(it + 1);  // runs under the W2 conversion below
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       float v[16];
       tmem_ld16(tmem + lane_addr + TM_W2 + 64 * half + 16 * c, reinterpret_cast<uint32_t*>(v));
       tc_wait_ld();
-      st_row16(sbase + SM_W2B, j, 2 * c, v);
+      st_row16_op<kF16>(sbase + SM_W2B, j, 2 * c, v);
+      if (store_img) st_image16(img_n + 32768, j, 2 * c, v);
     }
     if (store_img) {
       b1img[(size_t)(it + 1) * HID + j] = b1r;
@@ -370,13 +416,8 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (warp_u == 0 && elect_one()) {
-      if (store_img) bulk_store_1d(img + (size_t)(it + 1) * 65536 + 32768, smem + SM_W2B, 32768);
-      bulk_commit();
-    }
   }
 
-  if (warp_u == 0 && elect_one()) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -403,12 +444,14 @@ cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const 
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
   bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
-    TB_TRY(cudaFuncSetAttribute(traj::ttt_mlp_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, traj::SM_TOTAL), "smem attr (traj)");
+    TB_TRY(cudaFuncSetAttribute(traj::ttt_mlp_traj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, traj::SM_TOTAL), "smem attr (traj)");
+    TB_TRY(cudaFuncSetAttribute(traj::ttt_mlp_traj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, traj::SM_TOTAL), "smem attr (traj)");
     attr_done = true;
   }
   g_where = "trajectory launch";
   const dim3 grid(B * H, (t_end - t0 + G - 1) / G);
-  traj::ttt_mlp_traj_kernel<<<grid, traj::NT, traj::SM_TOTAL, stream>>>(tk, tv, p);
+  if (mlp_operands_bf16()) traj::ttt_mlp_traj_kernel<false><<<grid, traj::NT, traj::SM_TOTAL, stream>>>(tk, tv, p);
+  else                     traj::ttt_mlp_traj_kernel<true><<<grid, traj::NT, traj::SM_TOTAL, stream>>>(tk, tv, p);
   return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@
 //   mode 6: as mode 1 but only rows 0-63 of A are staged and LBO = 0: rows 64-127 of D must duplicate rows 0-63
 //   mode 7: A from TMEM ("TS" form: row m of A on TMEM lane m, two bf16 per 32-bit column), B K-major in smem (K <= 128)
 //   mode 8: as mode 7 with B MN-major (N = 64)
+//   mode 9 / 10 / 11: as modes 0 / 1 / 2 with BOTH operands fp16 (the operand format of the TTT-MLP forward-type GEMMs)
 #include "ptx.cuh"
 #include "ttt_internal.h"
 
@@ -41,8 +42,8 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
     const int m = idx / K, k = idx % K;
     uint32_t off;
     if (mode == 6 && m >= 64) continue;
-    if (mode >= 7) break;  // A goes to TMEM below
-    if (mode == 1 || mode == 5 || mode == 6) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
+    if (mode == 7 || mode == 8) break;  // A goes to TMEM below
+    if (mode == 1 || mode == 5 || mode == 6 || mode == 10) off = (uint32_t)(m >> 6) * (uint32_t)K * 128u + elem_off(k, m & 63);
     else           off = (uint32_t)(k >> 6) * 16384u + elem_off(m, k & 63);
     *reinterpret_cast<__nv_bfloat16*>(smem + off) = A[idx];
   }
@@ -51,7 +52,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
     for (int idx = tid; idx < K * N; idx += 128) {
       const int k = idx / N, n = idx % N;
       uint32_t off;
-      if (mode == 0 || mode == 4 || mode == 7) off = (uint32_t)(k >> 6) * (uint32_t)N * 128u + elem_off(n, k & 63);
+      if (mode == 0 || mode == 4 || mode == 7 || mode == 9) off = (uint32_t)(k >> 6) * (uint32_t)N * 128u + elem_off(n, k & 63);
       else           off = elem_off(k, n);
       *reinterpret_cast<__nv_bfloat16*>(smB + off) = Bm[idx];
     }
@@ -67,7 +68,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
   if (mode == 3) mbar_wait(&bar[1], 0);
   const uint32_t tmem = tmem_ptr;
   constexpr uint32_t TM_A = 128;  // A operand columns of the TS modes
-  if (mode >= 7) {  // row tid of A -> TMEM lane tid, K/2 packed columns
+  if (mode == 7 || mode == 8) {  // row tid of A -> TMEM lane tid, K/2 packed columns
     const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + (size_t)tid * K);
     for (int c = 0; c < K / 2; c += 16) {
       uint32_t v[16];
@@ -80,7 +81,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
     tc_fence_after();
   }
 
-  if (tid == 0 && mode >= 7) {
+  if (tid == 0 && (mode == 7 || mode == 8)) {
     const bool b_mn = (mode == 8);
     const uint32_t idesc = make_idesc_bf16(128, N, false, b_mn);
     for (int k16 = 0; k16 < K / 16; ++k16) {
@@ -91,9 +92,9 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
     }
     tc_commit(&bar[0]);
   }
-  if (tid == 0 && mode < 7) {
-    const bool a_mn = (mode == 1 || mode >= 5), b_mn = (mode == 1 || mode == 2 || mode >= 5);
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn, false, mode == 4 || mode == 5, false);
+  if (tid == 0 && (mode < 7 || mode >= 9)) {
+    const bool a_mn = (mode == 1 || mode == 5 || mode == 6 || mode == 10), b_mn = (mode == 1 || mode == 2 || mode == 5 || mode == 6 || mode >= 10);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn, false, mode == 4 || mode == 5 || mode >= 9, mode >= 9);
     for (int k16 = 0; k16 < K / 16; ++k16) {
       uint64_t da, db;
       if (a_mn) da = desc_advance(make_desc_sw128(sA, mode == 6 ? 0u : (uint32_t)K * 128u, 1024), 2048u * k16);
@@ -118,14 +119,14 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmB, int mode, const __
 }
 
 cudaError_t launch_umma_selftest(int mode, const void* A, const void* Bm, float* D, int N, int K, cudaStream_t stream) {
-  if (mode < 0 || mode > 8 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
-  if ((mode == 1 || mode == 2 || mode == 5 || mode == 6 || mode == 8) && N != 64) return cudaErrorInvalidValue;
-  if (mode >= 7 && K > 128) return cudaErrorInvalidValue;
+  if (mode < 0 || mode > 11 || K % 64 || K > 256 || N % 16 || N > 128) return cudaErrorInvalidValue;
+  if ((mode == 1 || mode == 2 || mode == 5 || mode == 6 || mode == 8 || mode == 10 || mode == 11) && N != 64) return cudaErrorInvalidValue;
+  if ((mode == 7 || mode == 8) && K > 128) return cudaErrorInvalidValue;
   if (mode == 3 && K != 64) return cudaErrorInvalidValue;
   CUtensorMap tm;
   // mode 3: Bm is given K-major already ([N][64] bf16); other modes do not dereference the map but it must be valid
   if (make_token_tmap(&tm, mode == 3 ? Bm : A, mode == 3 ? (uint64_t)N : 128ull)) return cudaErrorInvalidValue;
-  const size_t smem = 128 * (size_t)K * 2 + (size_t)((mode == 0 || mode == 3 || mode == 4 || mode == 7) ? N * K * 2 : K * 128);
+  const size_t smem = 128 * (size_t)K * 2 + (size_t)((mode == 0 || mode == 3 || mode == 4 || mode == 7 || mode == 9) ? N * K * 2 : K * 128);
   cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   umma_selftest_kernel<<<1, 128, smem, stream>>>(tm, mode, reinterpret_cast<const __nv_bfloat16*>(A),
