@@ -254,8 +254,93 @@ def gen_layer():
     torch.save(out, os.path.join(GOLD, "ttt_layer_ref.pt"))
 
 
+def gen_transformer_layer():
+    """The reference's whole ``TransformerLayer`` (adaLN shell + SeqModelingBlock: local attention, bidirectional gated
+    TTT-MLP, eager scan + autograd; dit.py:281-382), single scene and THREE scenes, fp64 on CPU.
+
+    Multi-scene eta semantics (SURVEY trap #1): ``interleave`` permutes the eta rows, the eager dual form reads the full
+    [CS, CS] eta (ops/ttt_mlp.py:40-46) while the native kernel path reads only the last row (mlp_tk.py:105).  Both are
+    recorded: ``ref`` / ``grads`` with the rows forced to the last row (what ``use_kernel=True`` computes: the semantics the
+    B200 kernels implement) and ``ref_full_eta`` as the module runs it eagerly, so the test can state the distance."""
+    import ttt.models.ssm.ttt_layer as ref_layer
+    from ttt.models.cogvideo.dit import TransformerLayer
+    from ttt.models.cogvideo.utils import SequenceMetadata
+    from ttt.models.configs import ModelConfig
+
+    eager_mlp = ref_layer.ttt_mlp
+
+    def last_row_eta(XK, XQ, XV, eta, *rest):
+        return eager_mlp(XK, XQ, XV, eta[:, :, :, -1:, :].expand_as(eta).contiguous(), *rest)
+
+    out = []
+    for frames, TL, chunks in ((13, 48, 1), (37, 16, 3)):
+        torch.manual_seed(100 + chunks)
+        E, NH, Hh, Ww, TE = 128, 2, 4, 4, 32
+        cfg = ModelConfig(model_dim=E, num_heads=NH, num_layers=1, ssm_layer="ttt_mlp", mini_batch_size=64, ttt_base_lr=0.1,
+                          latent_height=Hh, latent_width=Ww, compressed_num_frames=frames, adapter_method="sft",
+                          scan_checkpoint_group_size=2, time_embed_dim=TE)
+        layer = TransformerLayer(cfg).double()
+        layer.seq_modeling_block.ssm.ttt.use_kernel = False
+        layer.seq_modeling_block.ssm.init_freqs()
+        with torch.no_grad():
+            for n, p_ in layer.named_parameters():
+                if n.endswith((".W1", ".W2")):
+                    p_.copy_(torch.randn_like(p_) * 0.02)
+                elif n.endswith((".b1", ".b2")):
+                    p_.zero_()
+                elif "gating_alpha" in n:
+                    p_.copy_(0.1 + 0.05 * torch.randn_like(p_))
+                else:
+                    p_.copy_(torch.randn_like(p_) * (0.2 if p_.dim() == 1 else 0.06))
+            for m in (layer.pre_seq_layernorm, layer.pre_mlp_layernorm, layer.seq_modeling_block.q_norm, layer.seq_modeling_block.k_norm,
+                      layer.seq_modeling_block.ssm.ttt.post_norm):
+                m.weight.add_(1.0)
+            layer.seq_modeling_block.ssm.ttt.ttt_norm_weight.add_(1.0)
+        tpf = Hh * Ww
+        B, Lv, Lt = 2, frames * tpf, TL * chunks
+        assert (Lv + Lt) % 64 == 0
+        t_emb = torch.randn(B, TE, dtype=torch.float64)
+        md = SequenceMetadata(text_length=TL, seq_text_length=Lt, num_frames=frames, num_chunks=chunks, tokens_per_frame=tpf,
+                              latent_height=Hh, latent_width=Ww, t_emb=t_emb)
+        md.init_multiscene_offsets()
+        vid = torch.randn(B, Lv, E, dtype=torch.float64, requires_grad=True)
+        txt = torch.randn(B, Lt, E, dtype=torch.float64, requires_grad=True)
+        with torch.no_grad():
+            v_full, t_full = layer(vid, txt, md)
+        blk_out = {}
+        hook = layer.seq_modeling_block.register_forward_hook(lambda m, i, o: blk_out.update(vid=o[0].detach(), txt=o[1].detach(), x_vid=i[0].detach(), x_txt=i[1].detach()))
+        ref_layer.ttt_mlp = last_row_eta
+        try:
+            v_ref, t_ref = layer(vid, txt, md)
+            gv = torch.randn_like(v_ref); gt = torch.randn_like(t_ref)
+            (v_ref * gv).sum().add((t_ref * gt).sum()).backward()
+        finally:
+            ref_layer.ttt_mlp = eager_mlp
+            hook.remove()
+        keep = ("pre_seq_adaLN_modulation.1.weight", "pre_seq_layernorm.weight", "seq_modeling_block.q.weight", "seq_modeling_block.o.bias",
+                "seq_modeling_block.k_norm.weight", "seq_modeling_block.ssm.ttt.W1", "seq_modeling_block.ssm.ttt.b2",
+                "seq_modeling_block.ssm.ttt.wq.weight", "seq_modeling_block.ssm.ttt.ttt_norm_weight",
+                "seq_modeling_block.ssm.ttt.learnable_ttt_lr_weight", "seq_modeling_block.ssm.ttt.post_norm.weight",
+                "seq_modeling_block.forward_ssm_gating_video.gating_alpha", "seq_modeling_block.backward_ssm_gating_text.gating_alpha",
+                "mlp.layer1.weight", "mlp.layer2.bias", "pre_mlp_adaLN_modulation.1.bias")
+        named = dict(layer.named_parameters())
+        f = lambda t: t.detach().float()
+        out.append(dict(cfg=dict(E=E, NH=NH, Hh=Hh, Ww=Ww, frames=frames, TL=TL, chunks=chunks, B=B, TE=TE, CS=64, base_lr=0.1, group=2,
+                                 attn_length=cfg.attn_length, prefix=cfg.prefix_temporal_length, ln_eps=cfg.layer_norm_eps),
+                        vid=f(vid), txt=f(txt), t_emb=f(t_emb), P={k: f(v) for k, v in layer.state_dict().items()},
+                        ref_vid=f(v_ref), ref_txt=f(t_ref), ref_full_eta_vid=f(v_full), ref_full_eta_txt=f(t_full),
+                        block_in_vid=f(blk_out["x_vid"]), block_in_txt=f(blk_out["x_txt"]), block_vid=f(blk_out["vid"]), block_txt=f(blk_out["txt"]),
+                        gout_vid=f(gv), gout_txt=f(gt), grads=dict({k: f(named[k].grad) for k in keep}, vid=f(vid.grad), txt=f(txt.grad)),
+                        eta_semantics_distance=O.rel_err(torch.cat((t_full, v_full), 1), torch.cat((t_ref, v_ref), 1))))
+        print(f"transformer layer ({chunks} scene(s)) ok; full-eta vs last-row-eta output distance = {out[-1]['eta_semantics_distance']:.3e}")
+    torch.save(out, os.path.join(GOLD, "transformer_layer_ref.pt"))
+
+
 if __name__ == "__main__":
     assert os.path.isdir("/root/reference/ttt"), "the reference is only present in the build container"
+    if len(sys.argv) > 1 and sys.argv[1] == "transformer_layer":
+        gen_transformer_layer()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "process_input":
         gen_process_input()
         sys.exit(0)
@@ -267,5 +352,6 @@ if __name__ == "__main__":
     gen_block()
     gen_process_input()
     gen_layer()
+    gen_transformer_layer()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -5,4 +5,4 @@ Public surface mirrors the reference:
   mlp_tk.TkMLP (torch.autograd.Function)             <-> ttt/models/ssm/mlp_tk.py:9
 """
 __all__ = ["_lib", "test_time_training", "mlp_tk", "linear_triton", "seq_block", "seq_shard", "attention", "process_input",
-           "ttt_layer", "interleave", "host_stream"]
+           "ttt_layer", "interleave", "host_stream", "rope", "transformer_layer"]
