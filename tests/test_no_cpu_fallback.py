@@ -15,7 +15,7 @@ bf = lambda t: t.to(torch.bfloat16)
 
 
 def test_every_public_op_refuses_host_tensors():
-    from ttt_video_dit_b200 import attention, linear_triton, mlp_tk, process_input, seq_block
+    from ttt_video_dit_b200 import attention, linear_triton, mlp_tk, process_input, seq_block, transformer_layer
     d = O.make_inputs(1, 2, 2, seed=0)
     prm = [d[k] for k in ("ln_w", "ln_b", "W1", "b1", "W2", "b2")]
     dl = O.make_inputs(1, 2, 2, CS=16, seed=0, base_lr=1.0, linear=True)
@@ -32,6 +32,8 @@ def test_every_public_op_refuses_host_tensors():
                                                  torch.ones(2, 64), torch.zeros(2, 64), 0, 64, 0.1),
         "output_norm": lambda: process_input.output_norm(bf(torch.randn(1, 2, 2, 64, 64)), torch.ones(128), torch.zeros(128)),
         "ssm_forward": lambda: seq_block.ssm_forward(x, lambda t: t, 0, 1, False, gate, gate, gate, gate),
+        "LnAffine": lambda: transformer_layer.LnAffine.apply(x, torch.ones(1, 2, 128), torch.zeros(1, 2, 128), 0, 1e-6),
+        "GateAdd": lambda: transformer_layer.GateAdd.apply(x, x, torch.ones(1, 2, 128), 0),
     }
     for name, fn in calls.items():
         with pytest.raises(RuntimeError, match="CUDA"):
