@@ -20,6 +20,11 @@ int ttt_b200_debug_umma(int mode, const void* A_bf16, const void* B_bf16, float*
 int ttt_b200_debug_spin(int blocks, int threads, long long cycles, int mode, int smem_bytes, float* sink,
                         long long sink_floats, void* stream);
 
+/* Distributed-shared-memory microbenchmark (csrc/dsmem_probe.cu): out[0] (device float) = cycles of ONE one-way transfer of
+ * `bytes` between the two CTAs of a cluster including the completion signal (ping-pong / 2).  mode 0 = one
+ * cp.async.bulk.shared::cluster copy, 1 = st.shared::cluster.v4 by 256 threads, 2 = four bulk copies back to back. */
+int ttt_b200_debug_dsmem(int mode, int bytes, int iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,7 @@ DEBUG_LIB_PATH = os.environ.get("TTT_B200_SELFTEST_LIB") or os.path.join(_HERE, 
 _DEBUG_SIGS = {
     "ttt_b200_debug_last_error": ([], ctypes.c_char_p),
     "ttt_b200_debug_umma": ([_i, _vp, _vp, _fp, _i, _i, _vp], ctypes.c_int),
+    "ttt_b200_debug_dsmem": ([_i, _i, _i, _fp, _vp], ctypes.c_int),
     "ttt_b200_debug_spin": ([_i, _i, ctypes.c_longlong, _i, _i, _fp, ctypes.c_longlong, _vp], ctypes.c_int),
 }
 _debug_lib = None

@@ -11,8 +11,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libttt_b200.so")
 SELFTEST_LIB = os.path.join(LIBDIR, "libttt_b200_selftest.so")  # include/ttt_b200_debug.h: development probes only
-SELFTEST_SRC = ("umma_selftest.cu", "capi_debug.cu", "tmap.cu")   # tmap.cu is shared with the production library
-PROD_EXCLUDE = ("umma_selftest.cu", "capi_debug.cu")
+SELFTEST_SRC = ("umma_selftest.cu", "dsmem_probe.cu", "capi_debug.cu", "tmap.cu")   # tmap.cu is shared with the production library
+PROD_EXCLUDE = ("umma_selftest.cu", "dsmem_probe.cu", "capi_debug.cu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

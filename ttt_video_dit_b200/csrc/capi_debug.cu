@@ -26,4 +26,12 @@ int ttt_b200_debug_spin(int blocks, int threads, long long cycles, int mode, int
                   "ttt_b200_debug_spin");
 }
 
+// Distributed-shared-memory microbenchmark (csrc/dsmem_probe.cu): out[0] = cycles of one one-way transfer of `bytes` between the
+// CTAs of a 2-CTA cluster including the completion signal.  mode 0 = bulk copy, 1 = st.shared::cluster, 2 = 4 bulk copies.
+int ttt_b200_debug_dsmem(int mode, int bytes, int iters, float* out, void* stream) {
+  if (!out) return fail(-1, "ttt_b200_debug_dsmem: null pointer argument");
+  TB_BIND_DEVICE(out);
+  return cuda_ret(tb::launch_dsmem_probe(mode, bytes, iters, out, (cudaStream_t)stream), "ttt_b200_debug_dsmem");
+}
+
 }  // extern "C"

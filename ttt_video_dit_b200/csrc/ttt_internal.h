@@ -147,3 +147,7 @@ cudaError_t launch_gate_add(const void* x, const void* y, const float* G, void* 
 cudaError_t launch_gate_add_backward(const void* gout, const void* y, const float* G, void* dy, float* dG, int B, int L, int E,
                                      int text_len, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_dsmem_probe(int mode, int bytes, int iters, float* out, cudaStream_t stream);
+}  // namespace tb
