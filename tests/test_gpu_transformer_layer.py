@@ -76,3 +76,25 @@ def test_transformer_layer_backward_matches_autograd_of_reference(which):
             errs[n] = O.rel_err(P[n].grad.float().cpu().reshape(g.shape), g)
     bad = {k: v for k, v in errs.items() if not (v < 6e-2)}
     assert not bad, (fx["cfg"]["chunks"], bad, errs)
+
+
+def test_sampling_stack_batched_guidance_pair_and_cuda_graph():
+    """f4: the classifier-free-guidance pair as one batch of 2 through a 2-layer stack == the reference's per-element loop
+    (cogvideo/utils.py:478-489) up to GEMM tiling, and a CUDA-graph replay of the stack == the eager launch sequence."""
+    from ttt_video_dit_b200 import sampling
+    fx = torch.load(GOLD, weights_only=False)[1]  # 3 scenes
+    meta, P = _setup(fx)
+    layers = [P, P]
+    emb = torch.cat((fx["txt"], fx["vid"]), dim=1).to(torch.bfloat16).cuda()  # B = 2: stands for (unconditional, conditional)
+    t_emb = fx["t_emb"].cuda()
+    both = sampling.dit_stack_forward(emb, t_emb, layers, meta)
+    one_by_one = torch.cat([sampling.dit_stack_forward(emb[i:i + 1].contiguous(), t_emb[i:i + 1], layers, meta) for i in range(2)])
+    torch.cuda.synchronize()
+    assert O.rel_err(both.float().cpu(), one_by_one.float().cpu()) < 2e-2
+    graphed = sampling.GraphedCall(lambda e, t: sampling.dit_stack_forward(e, t, layers, meta), emb, t_emb)
+    out = graphed(emb, t_emb)
+    torch.cuda.synchronize()
+    assert torch.equal(out, both)
+    out2 = graphed(emb.flip(0).contiguous(), t_emb.flip(0).contiguous())  # new inputs through the same captured graph
+    torch.cuda.synchronize()
+    assert O.rel_err(out2.flip(0).float().cpu(), both.float().cpu()) < 2e-2
