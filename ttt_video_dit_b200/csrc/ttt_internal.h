@@ -55,7 +55,8 @@ bool mlp_operands_bf16();  // TTT_B200_OPERANDS=bf16: bf16 instead of fp16 opera
 cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                           const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
                                           const float* b2c, int B, int H, int NC, int K, int G, int t0, int t_end,
-                                          uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream);
+                                          uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream,
+                                          const unsigned* wait_done = nullptr);
 size_t mlp_backward_workspace_bytes(int B, int H, int G);
 cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                 const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
@@ -104,7 +105,7 @@ namespace tb {
 cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo, const float* ln_w, const float* ln_b,
                                   const uint8_t* img, const float* b1img, const float* b2img, uint8_t* qt, float* qb1,
                                   float* qb2, void* dXQ, int BH, int H, int NC, int img_slots,
-                                  int G, int t0, int nsteps, cudaStream_t stream);
+                                  int G, int t0, int nsteps, cudaStream_t stream, unsigned* ready = nullptr);
 }  // namespace tb
 
 namespace tb {

@@ -45,25 +45,53 @@ constexpr uint32_t TM_DW1 = 0;    // dW1^T accumulator, + 64*h
 constexpr uint32_t TM_DW2 = 128;  // dW2   accumulator, + 64*h
 constexpr uint32_t TM_S0 = 256, TM_S1 = 320, TM_S2 = 384, TM_S3 = 448;  // working slots of 64 columns
 
+constexpr int kRingSlots = 3;  // recompute buffers in flight (kRing of the host orchestrator)
+
 struct BwdParams {
   const __nv_bfloat16* last_eta;  // [B,H,NC,64]
   const float *ln_w, *ln_b;       // [H,64]
-  const uint8_t* img;             // [BH][img_slots] x 64 KB  {W1^T image, W2 image}
-  const float *b1img, *b2img;     // [BH][img_slots][256], [BH][img_slots][64]
+  // Recompute buffers of the checkpoint groups, a ring of kRingSlots: group g (steps [g*G, (g+1)*G)) is processing unit
+  // u = K-1-g and lives in ring slot u % kRingSlots; inside a slot, step t is local index t - g*G.
+  const uint8_t* img[kRingSlots];             // [BH][img_slots] x 64 KB  {W1^T image, W2 image} of the state entering each step
+  const float *b1img[kRingSlots], *b2img[kRingSlots];  // [BH][img_slots][256], [BH][img_slots][64]
+  const uint8_t* qt[kRingSlots];              // Q-side factor tiles [BH][G] x 73728 B (ttt_mlp_bwd_q.cu)
+  const float *qb1[kRingSlots], *qb2[kRingSlots];      // Q-side contributions [BH][G][256] (d b1), [BH][G][192] = {d b2, d gamma, d beta}
   float *dW1s, *dW2s, *db1s, *db2s;  // carried state gradient, fp32: [BH][256][64] x2, [BH][256], [BH][64]
   uint8_t* x2spill;                  // [BH][32 KB]
-  const uint8_t* qt;                 // Q-side factor tiles [BH][G] x 73728 B (ttt_mlp_bwd_q.cu)
-  const float *qb1, *qb2;            // Q-side contributions [BH][G][256] (d b1), [BH][G][192] = {d b2, d gamma, d beta}
-  int G;
+  int G, K;                          // steps per checkpoint group, number of groups
   __nv_bfloat16 *dXQ, *dXK, *dXV, *dEta;  // outputs
   float *dlnw, *dlnb;                     // [BH][64], accumulated launch after launch, one writer per element (pre-zeroed by the host)
-  float *dW1, *db1, *dW2, *db2;           // final gradient w.r.t. the initial state (written when t_lo == 0)
+  float *dW1, *db1, *dW2, *db2;           // final gradient w.r.t. the initial state (written when the launch ends at step 0)
   int H, NC, img_slots;
-  int t_hi, t_lo, t0;  // iterations t_hi..t_lo (descending); image slot of W_t is t - t0
+  int t_hi, t_lo;      // iterations t_hi..t_lo (descending).  Persistent mode: the whole scan in ONE launch (NC-1 .. 0)
   int first;           // 1: start from zero state gradient, 0: load it from the scratch
+  // Persistent mode (both non-null): device-side hand-shake with the recompute kernels running on other SMs.
+  //   ready[u * BH + bh] counts the Q-side CTAs of unit u, sequence bh, that have finished (the unit's images are complete
+  //   before its Q-side kernel starts); the K-side CTA waits for the unit's step count before touching the unit's buffers.
+  //   done[u * BH + bh] is set by the K-side CTA after its last access to unit u: the trajectory kernel of unit
+  //   u + kRingSlots (same ring slot) waits for it before overwriting.
+  const unsigned* ready;
+  unsigned* done;
   unsigned* dbg;       // phase-timing buffer (debug builds)
   int dbg_group;       // group (t_lo / G) whose observer phase times are dumped
 };
+
+// Bounded spin on a device-side counter written by another kernel (acquire at gpu scope).  A protocol bug must surface as a
+// launch failure (trap), never as a hung GPU.
+static __device__ __noinline__ void wait_counter(const unsigned* ctr, unsigned want) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= want) break;
+    __nanosleep(256);
+    if (clock64() - t0 > 20000000000LL) {
+      printf("ttt_b200: device-side flag wait timed out (block %d thread %d, have %u want %u)\n", (int)blockIdx.x, (int)threadIdx.x, v, want);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // the data behind the flag is read by bulk / TMA loads (async proxy) too
+}
 
 __global__ void __launch_bounds__(NT, 1)
 ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -137,30 +165,44 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  const uint8_t* img_bh = p.img + (size_t)bh * p.img_slots * 65536;
   const size_t row_bh = (size_t)bh * p.NC * CS;  // token row of step 0 of this sequence
+  // ring addressing of the per-step recompute data (see BwdParams)
+  auto ring_of = [&](int t, int& local) { const int g = t / p.G; local = t - g * p.G; return (p.K - 1 - g) % kRingSlots; };
+  auto img_of = [&](int t) { int l; const int r = ring_of(t, l); return p.img[r] + ((size_t)bh * p.img_slots + l) * 65536; };
+  auto qt_of = [&](int t) { int l; const int r = ring_of(t, l); return p.qt[r] + ((size_t)bh * p.G + l) * 73728; };
+  auto b1img_of = [&](int t) { int l; const int r = ring_of(t, l); return p.b1img[r] + ((size_t)bh * p.img_slots + l) * HID; };
+  auto b2img_of = [&](int t) { int l; const int r = ring_of(t, l); return p.b2img[r] + ((size_t)bh * p.img_slots + l) * F; };
+  auto qb1_of = [&](int t) { int l; const int r = ring_of(t, l); return p.qb1[r] + ((size_t)bh * p.G + l) * HID; };
+  auto qb2_of = [&](int t) { int l; const int r = ring_of(t, l); return p.qb2[r] + ((size_t)bh * p.G + l) * 192; };
+  // persistent mode: before the first access to the buffers of the unit that holds step t
+  auto wait_unit_of = [&](int t) {
+    if (p.ready == nullptr) return;
+    const int g = t / p.G, u = p.K - 1 - g;
+    const int steps = min(p.NC, (g + 1) * p.G) - g * p.G;
+    wait_counter(p.ready + (size_t)u * gridDim.x + bh, (unsigned)steps);
+  };
 
   // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
   uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
   uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0, ph_aux = 0, ph_xb = 0;
 
-  const uint8_t* qt_bh = p.qt + (size_t)bh * p.G * 73728;
   // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t.  Thread 0 only.
   auto load_xb = [&](int t, uint32_t xs) {  // Xbar2^T factor tile of step t
     mbar_expect_tx(bar_xb, 32768);
-    bulk_load_1d(smem + xs, qt_bh + (size_t)(t - p.t0) * 73728, 32768, bar_xb);
+    bulk_load_1d(smem + xs, qt_of(t), 32768, bar_xb);
   };
   auto load_q_rest = [&](int t, uint32_t zs) {  // Q_t tile, dZbar1^T -> slot zs, dZbar2 -> TT0
-    const uint8_t* src = qt_bh + (size_t)(t - p.t0) * 73728;
+    const uint8_t* src = qt_of(t);
     mbar_expect_tx(bar_qd, 8192 + 32768 + 8192);
     tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)t * CS), bar_qd);
     bulk_load_1d(smem + zs, src + 32768, 32768, bar_qd);
     bulk_load_1d(smem + SM_TT0, src + 65536, 8192, bar_qd);
   };
   // first iteration's loads, issued before the carried gradient is read so that both latencies overlap
+  wait_unit_of(p.t_hi);
   if (warp_u == 0 && elect_one()) {
     const int t = p.t_hi;
-    const uint8_t* im = img_bh + (size_t)(t - p.t0) * 65536;
+    const uint8_t* im = img_of(t);
     mbar_expect_tx(bar_w1, 32768);
     bulk_load_1d(smem + sW1, im, 32768, bar_w1);
     mbar_expect_tx(bar_w2, 32768);
@@ -201,19 +243,18 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
-  float nb1 = p.b1img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * HID + j], nb2 = 0.f;
-  float nq1 = p.qb1[((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * HID + j], nq2 = 0.f, nqg = 0.f, nqb = 0.f;
+  float nb1 = b1img_of(p.t_hi)[j], nb2 = 0.f;
+  float nq1 = qb1_of(p.t_hi)[j], nq2 = 0.f, nqg = 0.f, nqb = 0.f;
   unsigned short neta = 0;
   if (tid < 64) {
-    nb2 = p.b2img[((size_t)bh * p.img_slots + (size_t)(p.t_hi - p.t0)) * F + tid];
-    const float* q2 = p.qb2 + ((size_t)bh * p.G + (size_t)(p.t_hi - p.t0)) * 192;
+    nb2 = b2img_of(p.t_hi)[tid];
+    const float* q2 = qb2_of(p.t_hi);
     nq2 = q2[tid]; nqg = q2[64 + tid]; nqb = q2[128 + tid];
     if (p.t_hi < p.NC) neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)p.t_hi * CS + tid];
   }
   TICK(14);  // prologue
   for (int t = p.t_hi; t >= p.t_lo; --t) {
     const bool has_k = true;
-    const size_t slot = (size_t)(t - p.t0);
     // per-iteration small vectors were prefetched into registers during the previous iteration (nb1/nb2/neta)
     const float b1t = nb1;
     const float q1t = nq1;
@@ -228,12 +269,12 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     db1r += q1t;         // ... and to d b1
     if (t > p.t_lo) {  // prefetch for iteration t-1
-      const size_t ns = slot - 1;
-      nb1 = p.b1img[((size_t)bh * p.img_slots + ns) * HID + j];
-      nq1 = p.qb1[((size_t)bh * p.G + ns) * HID + j];
+      if (t % p.G == 0) wait_unit_of(t - 1);  // step t-1 opens the next unit (persistent mode): its recompute must be complete
+      nb1 = b1img_of(t - 1)[j];
+      nq1 = qb1_of(t - 1)[j];
       if (tid < 64) {
-        nb2 = p.b2img[((size_t)bh * p.img_slots + ns) * F + tid];
-        const float* q2 = p.qb2 + ((size_t)bh * p.G + ns) * 192;
+        nb2 = b2img_of(t - 1)[tid];
+        const float* q2 = qb2_of(t - 1);
         nq2 = q2[tid]; nqg = q2[64 + tid]; nqb = q2[128 + tid];
         neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)(t - 1) * CS + tid];
       }
@@ -435,7 +476,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (warp_u == 0 && elect_one()) {  // sA (CW1) and sC (G1eta) are free: reload the W1 image and the X2 tile
         bulk_wait<0>();
         mbar_expect_tx(bar_w1r, 32768);
-        bulk_load_1d(smem + sA, img_bh + slot * 65536, 32768, bar_w1r);
+        bulk_load_1d(smem + sA, img_of(t), 32768, bar_w1r);
         mbar_expect_tx(bar_x2, 32768);
         bulk_load_1d(smem + sC, p.x2spill + (size_t)bh * 32768, 32768, bar_x2);
       }
@@ -542,7 +583,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       TICK(10);
       if (warp_u == 0 && (t > p.t_lo) && elect_one()) {  // the W2 image buffer is free now: fetch the next one
         mbar_expect_tx(bar_w2, 32768);
-        bulk_load_1d(smem + SM_W2I, img_bh + (size_t)(t - 1 - p.t0) * 65536 + 32768, 32768, bar_w2);
+        bulk_load_1d(smem + SM_W2I, img_of(t - 1) + 32768, 32768, bar_w2);
       }
       // ===== A10 [H]: dZ1 = dX2 * gelu'(Z1) + term2 -> sB ; d b1 += sum dZ1
       {
@@ -568,7 +609,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_aux, ph_aux); ph_aux ^= 1;   // DG1 (sW1) and X2 (sC) are no longer read by any MMA
       if (warp_u == 0 && (t > p.t_lo) && elect_one()) {
         mbar_expect_tx(bar_w1, 32768);
-        bulk_load_1d(smem + sC, img_bh + (size_t)(t - 1 - p.t0) * 65536, 32768, bar_w1);
+        bulk_load_1d(smem + sC, img_of(t - 1), 32768, bar_w1);
         load_xb(t - 1, sW1);
       }
       PHASE_SYNC();
@@ -594,6 +635,13 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       TICK(13);
     }
 
+    // persistent mode: step t was the last access to its unit's recompute buffers -> the trajectory kernel that refills this
+    // ring slot (unit u + kRingSlots) may start (every bulk load of the unit has completed and was consumed above)
+    if (p.done != nullptr && t % p.G == 0 && tid == 0) {
+      const int u = p.K - 1 - t / p.G;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + (size_t)u * gridDim.x + bh), "r"(1u) : "memory");
+    }
     // next iteration's remaining loads (buffers last used by the A11 batch): K/V tiles, Q tile, dZbar1^T -> sA, dZbar2 -> TT0
     const bool more = t > p.t_lo;
     if (warp_u == 0 && (more) && elect_one()) {
@@ -684,18 +732,24 @@ __global__ void seed_state_grad_kernel(const float* __restrict__ dW1u, const flo
 }  // namespace bwd
 
 // ------------------------------------------------------------------------------------------------ host
-// Recompute state is kept in a ring of kRing buffers so that the trajectory / Q-side kernels of later steps run ahead
-// of the sequential K-side kernel (three streams).  One K-side launch ("unit") may cover up to kSuper checkpoint groups
-// (the trajectory kernel then replays the groups of a unit concurrently, one CTA per (sequence, group)).  Measured on
-// B200 (profiles/r01_launch_units.log): units of 2-3 groups save the ~50 us per-launch cost but lose more to a longer
-// pipeline fill and to trajectory CTAs that take the SMs the next K-side launch is waiting for, so kSuper = 1.
-constexpr int kRing = 3;
-constexpr int kSuper = 1;
+// Recompute state is kept in a ring of kRing buffers so that the trajectory / Q-side kernels of later units run ahead of the
+// sequential K-side kernel (three streams).  A unit = one checkpoint group, processed last group first.
+//
+// Persistent mode (default when 2 * B*H + 16 <= SM count): ONE K-side launch walks all units; the recompute kernels run
+// beside it on the other SMs and the three kernels hand-shake through device-side counters (BwdParams::ready / done)
+// instead of host events -- no per-group launch gap, no carried-gradient round trip through global memory, no cold
+// instruction fetch per group (measured round 1: ~54 us per group of 16 steps, 19 % of the backward).  All recompute
+// launches are enqueued up front: a trajectory kernel whose ring slot is still in use spins (bounded, traps on timeout)
+// until the K-side CTA of its sequence releases the slot.  The SM-count condition keeps SMs free for the Q-side kernel
+// while B*H K-side CTAs and up to B*H waiting trajectory CTAs are resident (one CTA of any of the three kernels fills an
+// SM); above it the launches are ordered per unit with events as in round 1 (TTT_B200_PERSISTENT=0 forces that mode).
+constexpr int kRing = bwd::kRingSlots;
+constexpr int kMaxUnits = 4096;
 
 size_t mlp_backward_workspace_bytes(int B, int H, int G) {
-  const size_t bh = (size_t)B * H, g = (size_t)G * kSuper, slots = g + 1;
+  const size_t bh = (size_t)B * H, g = (size_t)G, slots = g + 1;
   return bh * (kRing * (slots * 65536 + slots * 256 * 4 + slots * 64 * 4) + kRing * (g * 73728 + g * 1024 + g * 768) +
-               2 * 65536 + 1024 + 256 + 32768) + 1024;
+               2 * 65536 + 1024 + 256 + 32768 + 2 * (size_t)(kMaxUnits + 1) * sizeof(unsigned)) + 1024;
 }
 
 cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, const void* last_eta, const float* ln_w,
@@ -707,8 +761,9 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
                                 const float* db2_last) {
   if (B <= 0 || H <= 0 || NC <= 0 || G <= 0) { g_where = "bad sizes"; return cudaErrorInvalidValue; }
   if (workspace_bytes < mlp_backward_workspace_bytes(B, H, G)) { g_where = "workspace"; return cudaErrorInvalidValue; }
-  const int Gs = G * kSuper;  // steps per ring buffer = stride of the per-step scratch arrays
-  const size_t bh = (size_t)B * H, slots = (size_t)Gs + 1;
+  const size_t bh = (size_t)B * H, slots = (size_t)G + 1;
+  const int K = (NC + G - 1) / G;  // units = checkpoint groups
+  if (K > kMaxUnits) { g_where = "too many checkpoint groups"; return cudaErrorInvalidValue; }
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
   w = reinterpret_cast<uint8_t*>(((uintptr_t)w + 1023) & ~(uintptr_t)1023);
   uint8_t* img[kRing]; float *b1img[kRing], *b2img[kRing];
@@ -721,9 +776,11 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   float* db1s = reinterpret_cast<float*>(w); w += bh * 1024;
   float* db2s = reinterpret_cast<float*>(w); w += bh * 256;
   uint8_t* qt[kRing]; float *qb1[kRing], *qb2[kRing];   // Q-side factor tiles / vectors of a group
-  for (int i = 0; i < kRing; ++i) { qt[i] = w; w += bh * (size_t)Gs * 73728; }
-  for (int i = 0; i < kRing; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 1024; }
-  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)Gs * 768; }
+  for (int i = 0; i < kRing; ++i) { qt[i] = w; w += bh * (size_t)G * 73728; }
+  for (int i = 0; i < kRing; ++i) { qb1[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 1024; }
+  for (int i = 0; i < kRing; ++i) { qb2[i] = reinterpret_cast<float*>(w); w += bh * (size_t)G * 768; }
+  unsigned* ready = reinterpret_cast<unsigned*>(w); w += bh * (size_t)(kMaxUnits + 1) * sizeof(unsigned);  // [unit][bh]
+  unsigned* done = reinterpret_cast<unsigned*>(w);  w += bh * (size_t)(kMaxUnits + 1) * sizeof(unsigned);
 
   CUtensorMap tq, tk, tv, tdo;
   const uint64_t rows = (uint64_t)bh * NC * 64;
@@ -732,9 +789,13 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
       make_token_tmap(&tdo, dOut, rows)) return cudaErrorInvalidValue;  // g_where set by make_token_tmap
   std::lock_guard<std::mutex> enqueue_lock(device_enqueue_mutex());
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
+  static int sm_count_dev[64] = {};
   bool& attr_done = *device_once(attr_done_dev);
+  int dev = 0;
+  TB_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   if (!attr_done) {
     TB_TRY(cudaFuncSetAttribute(bwd::ttt_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SM_TOTAL), "smem attr");
+    TB_TRY(cudaDeviceGetAttribute(&sm_count_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev), "SM count");
     attr_done = true;
   }
   TB_TRY(cudaMemsetAsync(dlnw, 0, bh * 64 * sizeof(float), stream), "memset dlnw");
@@ -743,11 +804,9 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
   // three streams per device (created once): T = trajectory, Q = Q-side kernel, main = sequential K-side kernel
   struct Side {
     cudaStream_t sT = nullptr, sQ = nullptr;
-    cudaEvent_t fork = nullptr, evT[kRing] = {}, evQ[kRing] = {}, evR[kRing] = {};
+    cudaEvent_t fork = nullptr, joinT = nullptr, joinQ = nullptr, evT[kRing] = {}, evQ[kRing] = {}, evR[kRing] = {};
   };
   static Side sides[64];
-  int dev = 0;
-  TB_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   Side& sd = sides[dev & 63];
   if (!sd.sT) {
     int prio_lo = 0, prio_hi = 0;  // recompute work must never delay the CTAs of the sequential kernel: lowest priority
@@ -755,80 +814,94 @@ cudaError_t launch_mlp_backward(const void* XQ, const void* XK, const void* XV, 
     TB_TRY(cudaStreamCreateWithPriority(&sd.sT, cudaStreamNonBlocking, prio_lo), "side stream");
     TB_TRY(cudaStreamCreateWithPriority(&sd.sQ, cudaStreamNonBlocking, prio_lo), "side stream");
     TB_TRY(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming), "event");
+    TB_TRY(cudaEventCreateWithFlags(&sd.joinT, cudaEventDisableTiming), "event");
+    TB_TRY(cudaEventCreateWithFlags(&sd.joinQ, cudaEventDisableTiming), "event");
     for (int i = 0; i < kRing; ++i) {
       TB_TRY(cudaEventCreateWithFlags(&sd.evT[i], cudaEventDisableTiming), "event");
       TB_TRY(cudaEventCreateWithFlags(&sd.evQ[i], cudaEventDisableTiming), "event");
       TB_TRY(cudaEventCreateWithFlags(&sd.evR[i], cudaEventDisableTiming), "event");
     }
   }
-  const int K = (NC + G - 1) / G;
   static const int dbg_group_env = [] { const char* v = getenv("TTT_DBG_GROUP"); return v ? atoi(v) : 0; }();
-  static const int super_env = [] { const char* v = getenv("TTT_B200_SUPER"); return v ? atoi(v) : kSuper; }();
-  const int m = super_env < 1 ? 1 : (super_env > kSuper ? kSuper : super_env);
-  // units in processing order (descending steps): {first group, last group}; the first unit is the last group alone
-  int ulo[1 + 4096], uhi[1 + 4096], U = 0;
-  for (int g = K - 1; g >= 0;) {
-    const int lo = (U == 0) ? g : (g - m + 1 > 0 ? g - m + 1 : 0);
-    if (U > 4096) { g_where = "too many launch units"; return cudaErrorInvalidValue; }
-    ulo[U] = lo; uhi[U] = g; ++U;
-    g = lo - 1;
-  }
-  // unit u -> ring buffer r = u % kRing: trajectory (images of W_{t0} .. W_{t1}) on stream T, then the Q-side kernel
-  // (steps t0 .. t1-1) on stream Q
-  auto recompute = [&](int u) -> cudaError_t {
-    const int r = u % kRing;
-    const int t0 = ulo[u] * G;
-    const int t1 = ((uhi[u] + 1) * G < NC) ? (uhi[u] + 1) * G : NC;
-    cudaError_t e = launch_mlp_trajectory_compact(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, G, t0, t1,
-                                                  img[r], b1img[r], b2img[r], (int)slots, sd.sT);
-    if (e != cudaSuccess) return e;
-    if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;
-    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[r], b1img[r], b2img[r], qt[r], qb1[r], qb2[r], dXQ,
-                              (int)bh, H, NC, (int)slots, Gs, t0, t1 - t0, sd.sQ);
-    if (e != cudaSuccess) return e;
-    return cudaEventRecord(sd.evQ[r], sd.sQ);
-  };
+  static const int persistent_env = [] { const char* v = getenv("TTT_B200_PERSISTENT"); return v ? atoi(v) : 1; }();
+  const bool persistent = persistent_env != 0 && 2 * (int)bh + 16 <= sm_count_dev[dev & 63];
   const bool seeded = dW1_last != nullptr;
   if (seeded) {  // carried gradient starts from the upstream d/dW_last instead of zero
     bwd::seed_state_grad_kernel<<<(unsigned)bh, 256, 0, stream>>>(dW1_last, db1_last, dW2_last, db2_last, dW1s, dW2s, db1s, db2s);
     TB_TRY(cudaGetLastError(), "seed launch");
   }
+  if (persistent) {
+    TB_TRY(cudaMemsetAsync(ready, 0, bh * (size_t)K * sizeof(unsigned), stream), "memset ready flags");
+    TB_TRY(cudaMemsetAsync(done, 0, bh * (size_t)K * sizeof(unsigned), stream), "memset done flags");
+  }
+  // unit u = group K-1-u -> ring buffer r = u % kRing: trajectory (images of W_{t0} .. W_{t1}) on stream T, then the Q-side
+  // kernel (steps t0 .. t1-1) on stream Q
+  auto recompute = [&](int u) -> cudaError_t {
+    const int r = u % kRing, g = K - 1 - u;
+    const int t0 = g * G, t1 = ((g + 1) * G < NC) ? (g + 1) * G : NC;
+    const unsigned* wait_done = (persistent && u >= kRing) ? done + (size_t)(u - kRing) * bh : nullptr;
+    cudaError_t e = launch_mlp_trajectory_compact(XK, XV, last_eta, ln_w, ln_b, W1c, b1c, W2c, b2c, B, H, NC, K, G, t0, t1,
+                                                  img[r], b1img[r], b2img[r], (int)slots, sd.sT, wait_done);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventRecord(sd.evT[r], sd.sT)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(sd.sQ, sd.evT[r], 0)) != cudaSuccess) return e;
+    e = launch_mlp_backward_q(tq, tdo, ln_w, ln_b, img[r], b1img[r], b2img[r], qt[r], qb1[r], qb2[r], dXQ,
+                              (int)bh, H, NC, (int)slots, G, t0, t1 - t0, sd.sQ, persistent ? ready + (size_t)u * bh : nullptr);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(sd.evQ[r], sd.sQ);
+  };
+  bwd::BwdParams p{};
+  p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
+  p.ln_w = ln_w; p.ln_b = ln_b;
+  for (int i = 0; i < kRing; ++i) {
+    p.img[i] = img[i]; p.b1img[i] = b1img[i]; p.b2img[i] = b2img[i];
+    p.qt[i] = qt[i]; p.qb1[i] = qb1[i]; p.qb2[i] = qb2[i];
+  }
+  p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
+  p.x2spill = x2s;
+  p.G = G; p.K = K;
+  p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
+  p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = reinterpret_cast<__nv_bfloat16*>(dEta);
+  p.dlnw = dlnw; p.dlnb = dlnb;
+  p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
+  p.H = H; p.NC = NC; p.img_slots = (int)slots;
+  p.dbg_group = dbg_group_env;
+  p.dbg = g_timing_buf;  // observers: the launch whose t_lo / G equals TTT_DBG_GROUP; per-launch stamps are kept
+
   TB_TRY(cudaEventRecord(sd.fork, stream), "fork record");
   TB_TRY(cudaStreamWaitEvent(sd.sT, sd.fork, 0), "fork wait");
   TB_TRY(cudaStreamWaitEvent(sd.sQ, sd.fork, 0), "fork wait");
-  for (int i = 0; i < kRing && i < U; ++i) TB_TRY(recompute(i), "trajectory / Q launch");
+  for (int i = 0; i < kRing && i < K; ++i) TB_TRY(recompute(i), "trajectory / Q launch");
 
-  for (int u = 0; u < U; ++u) {
-    const int r = u % kRing;
-    const int t0 = ulo[u] * G;
-    const int t1 = ((uhi[u] + 1) * G < NC) ? (uhi[u] + 1) * G : NC;
-    TB_TRY(cudaStreamWaitEvent(stream, sd.evQ[r], 0), "wait Q-side");
-    bwd::BwdParams p{};
-    p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
-    p.ln_w = ln_w; p.ln_b = ln_b;
-    p.img = img[r]; p.b1img = b1img[r]; p.b2img = b2img[r];
-    p.dW1s = dW1s; p.dW2s = dW2s; p.db1s = db1s; p.db2s = db2s;
-    p.x2spill = x2s;
-    p.qt = qt[r]; p.qb1 = qb1[r]; p.qb2 = qb2[r]; p.G = Gs;
-    p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ); p.dXK = reinterpret_cast<__nv_bfloat16*>(dXK);
-    p.dXV = reinterpret_cast<__nv_bfloat16*>(dXV); p.dEta = reinterpret_cast<__nv_bfloat16*>(dEta);
-    p.dlnw = dlnw; p.dlnb = dlnb;
-    p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
-    p.H = H; p.NC = NC; p.img_slots = (int)slots;
-    p.t_hi = t1 - 1;
-    p.t_lo = t0; p.t0 = t0;
-    p.first = (u == 0 && !seeded) ? 1 : 0;
-    p.dbg_group = dbg_group_env;
-    p.dbg = g_timing_buf;  // observers: the launch whose t_lo / G equals TTT_DBG_GROUP; per-launch stamps are kept
+  if (persistent) {
+    p.t_hi = NC - 1; p.t_lo = 0;
+    p.first = seeded ? 0 : 1;
+    p.ready = ready; p.done = done;
     bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
-    TB_TRY(cudaGetLastError(), "reverse launch");
-    if (u + kRing < U) {  // ring buffer r is free again once this launch is done: recompute unit u + kRing into it
-      TB_TRY(cudaEventRecord(sd.evR[r], stream), "record reverse");
-      TB_TRY(cudaStreamWaitEvent(sd.sT, sd.evR[r], 0), "wait reverse");
-      TB_TRY(recompute(u + kRing), "trajectory / Q launch");
+    TB_TRY(cudaGetLastError(), "reverse launch (persistent)");
+    for (int u = kRing; u < K; ++u) TB_TRY(recompute(u), "trajectory / Q launch");  // each waits on-device for its ring slot
+  } else {
+    for (int u = 0; u < K; ++u) {
+      const int r = u % kRing, g = K - 1 - u;
+      TB_TRY(cudaStreamWaitEvent(stream, sd.evQ[r], 0), "wait Q-side");
+      p.t_hi = (((g + 1) * G < NC) ? (g + 1) * G : NC) - 1;
+      p.t_lo = g * G;
+      p.first = (u == 0 && !seeded) ? 1 : 0;
+      bwd::ttt_mlp_bwd_kernel<<<(unsigned)bh, bwd::NT, bwd::SM_TOTAL, stream>>>(tq, tk, tv, p);
+      TB_TRY(cudaGetLastError(), "reverse launch");
+      if (u + kRing < K) {  // ring buffer r is free again once this launch is done: recompute unit u + kRing into it
+        TB_TRY(cudaEventRecord(sd.evR[r], stream), "record reverse");
+        TB_TRY(cudaStreamWaitEvent(sd.sT, sd.evR[r], 0), "wait reverse");
+        TB_TRY(recompute(u + kRing), "trajectory / Q launch");
+      }
     }
   }
+  // join: later work on `stream` (and the next call, which reuses the side streams and this workspace) is ordered after
+  // everything enqueued on the side streams
+  TB_TRY(cudaEventRecord(sd.joinT, sd.sT), "join record");
+  TB_TRY(cudaEventRecord(sd.joinQ, sd.sQ), "join record");
+  TB_TRY(cudaStreamWaitEvent(stream, sd.joinT, 0), "join wait");
+  TB_TRY(cudaStreamWaitEvent(stream, sd.joinQ, 0), "join wait");
   return cudaSuccess;
 }
 

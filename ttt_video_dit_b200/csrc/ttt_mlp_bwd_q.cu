@@ -40,6 +40,7 @@ struct BwdQParams {
   float *qb1, *qb2;              // out: [BH][G][256] (sum_i dZbar1), [BH][G][192] = {sum_i dZbar2, d gamma, d beta of the step}
   __nv_bfloat16* dXQ;            // out
   int H, NC, img_slots, G, t0;   // step s = t0 + blockIdx.x uses image slot blockIdx.x + 1
+  unsigned* ready;               // persistent K-side mode: counter [BH] of this unit, +1 per finished CTA (may be null)
 };
 
 // rolled (code-size) versions of bwd_common.cuh's mma_hid (N = 64, B K-major, no accumulate) and mma_tok
@@ -253,9 +254,14 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int f = 0; f < 16; ++f) a[f] += d[f];
     st_global16(p.dXQ + (row + trow) * 64 + c0, a);
   }
-  if (warp_u == 0 && elect_one()) bulk_wait_read<0>();  // smem of the factor tiles must stay valid until the bulk stores have read it
+  // the factor tiles must have landed in global memory (not only been read out of smem) before this CTA is reported done
+  if (warp_u == 0 && elect_one()) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
+  if (p.ready != nullptr && tid == 0) {  // every thread's global stores precede the barrier above; release them at gpu scope
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.ready + bh), "r"(1u) : "memory");
+  }
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
@@ -264,7 +270,7 @@ ttt_mlp_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo, const float* ln_w, const float* ln_b,
                                   const uint8_t* img, const float* b1img, const float* b2img, uint8_t* qt, float* qb1,
                                   float* qb2, void* dXQ, int BH, int H, int NC, int img_slots,
-                                  int G, int t0, int nsteps, cudaStream_t stream) {
+                                  int G, int t0, int nsteps, cudaStream_t stream, unsigned* ready) {
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
   bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {
@@ -274,7 +280,7 @@ cudaError_t launch_mlp_backward_q(const CUtensorMap& tq, const CUtensorMap& tdo,
   bwd::BwdQParams p{};
   p.ln_w = ln_w; p.ln_b = ln_b; p.img = img; p.b1img = b1img; p.b2img = b2img;
   p.qt = qt; p.qb1 = qb1; p.qb2 = qb2; p.dXQ = reinterpret_cast<__nv_bfloat16*>(dXQ);
-  p.H = H; p.NC = NC; p.img_slots = img_slots; p.G = G; p.t0 = t0;
+  p.H = H; p.NC = NC; p.img_slots = img_slots; p.G = G; p.t0 = t0; p.ready = ready;
   dim3 grid(nsteps, BH);
   bwd::ttt_mlp_bwd_q_kernel<<<grid, 256, bwd::QS_TOTAL, stream>>>(tq, tdo, p);
   return cudaGetLastError();

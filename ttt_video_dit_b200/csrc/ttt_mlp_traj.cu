@@ -92,6 +92,9 @@ struct TrajParams {
   int NC, H, K, G, t0, t_end, img_slots;
   uint8_t* img;                         // [BH][img_slots] x 64 KB
   float *b1img, *b2img;                 // [BH][img_slots][256], [BH][img_slots][64]
+  // persistent K-side mode: [BH] flags of the unit that used this ring slot before; the CTA of sequence bh starts writing
+  // only after the K-side CTA of bh has released the slot (null: the host orders the launches with events instead)
+  const unsigned* wait_done;
 };
 
 template <bool kF16>
@@ -110,6 +113,22 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const int half = warp >> 2, j = tid;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
 
+  if (p.wait_done != nullptr) {  // bounded spin (trap on timeout): a protocol bug must not hang the GPU
+    if (tid == 0) {
+      const long long t0c = clock64();
+      for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_done + bh) : "memory");
+        if (v != 0) break;
+        __nanosleep(512);
+        if (clock64() - t0c > 20000000000LL) {
+          printf("ttt_b200: trajectory kernel timed out waiting for its ring slot (block %d)\n", (int)blockIdx.x);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
   float* b2s = reinterpret_cast<float*>(smem + SM_MISC);
   float* lnw = b2s + 64;
   float* lnb = lnw + 64;
@@ -428,7 +447,8 @@ ttt_mlp_traj_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const void* last_eta, const float* ln_w,
                                           const float* ln_b, const float* W1c, const float* b1c, const float* W2c,
                                           const float* b2c, int B, int H, int NC, int K, int G, int t0, int t_end,
-                                          uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream) {
+                                          uint8_t* img, float* b1img, float* b2img, int img_slots, cudaStream_t stream,
+                                          const unsigned* wait_done) {
   if (G <= 0 || t0 % G != 0 || t_end <= t0 || t_end > NC || t_end - t0 + 1 > img_slots) {
     g_where = "bad trajectory window";
     return cudaErrorInvalidValue;
@@ -440,7 +460,7 @@ cudaError_t launch_mlp_trajectory_compact(const void* XK, const void* XV, const 
   p.last_eta = reinterpret_cast<const __nv_bfloat16*>(last_eta);
   p.ln_w = ln_w; p.ln_b = ln_b; p.W1 = W1c; p.b1 = b1c; p.W2 = W2c; p.b2 = b2c;
   p.NC = NC; p.H = H; p.K = K; p.G = G; p.t0 = t0; p.t_end = t_end; p.img_slots = img_slots;
-  p.img = img; p.b1img = b1img; p.b2img = b2img;
+  p.img = img; p.b1img = b1img; p.b2img = b2img; p.wait_done = wait_done;
   static bool attr_done_dev[64] = {};  // function attributes (and side streams) are per device
   bool& attr_done = *device_once(attr_done_dev);
   if (!attr_done) {

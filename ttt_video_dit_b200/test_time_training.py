@@ -59,17 +59,24 @@ def ttt_forward(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1, b1, W2
 
 
 LAUNCHES_FWD = 1  # one persistent scan kernel per forward call
-_last_groups = [1]
+_last_call = {"groups": 1, "bh": 1, "seeded": False, "sms": 148}
 
 
-SUPER = 1  # checkpoint groups per backward launch unit (kSuper in csrc/ttt_mlp_bwd.cu)
+def backward_is_persistent(bh, sms):
+    """Mirror of the launcher's choice (csrc/ttt_mlp_bwd.cu): one K-side launch for the whole backward, hand-shaking with the
+    recompute kernels through device-side flags, while the SMs can hold B*H K-side CTAs + B*H waiting trajectory CTAs + a
+    few for the Q-side kernel; per-group launches ordered by events otherwise (or with TTT_B200_PERSISTENT=0)."""
+    import os
+    return os.environ.get("TTT_B200_PERSISTENT", "1") != "0" and 2 * bh + 16 <= sms
 
 
 def launches_bwd():
-    """2 memsets are library calls; our kernels per launch unit: trajectory + Q-side kernel + sequential K-side kernel."""
-    groups = _last_groups[0]
-    units = 1 + (groups - 1 + SUPER - 1) // SUPER
-    return 3 * units
+    """Our kernels of the last backward call: per checkpoint group one trajectory + one Q-side kernel, plus the sequential
+    K-side kernel -- once (persistent mode) or once per group -- plus the seed kernel of a chained call (the memsets are
+    library calls)."""
+    c = _last_call
+    k_side = 1 if backward_is_persistent(c["bh"], c["sms"]) else c["groups"]
+    return 2 * c["groups"] + k_side + (1 if c["seeded"] else 0)
 
 
 def _workspace(B, H, G, device):
@@ -113,7 +120,7 @@ def ttt_backward_simple(XQ, XK, XV, last_eta, ttt_norm_weight, ttt_norm_bias, W1
         p(dlw), p(dlb), p(dW1), p(db1), p(dW2), p(db2), p(de), p(dq), p(dk), p(dv), p(ws), n,
         B, H, NC, int(checkpoint_group_size), _lib.current_stream(XQ))
     _lib.check(code, "ttt_b200_mlp_backward")
-    _last_groups[0] = K
+    _last_call.update(groups=K, bh=B * H, seeded=dW_last is not None, sms=torch.cuda.get_device_properties(dev).multi_processor_count)
     return dlw.sum(0), dlb.sum(0), dW1, db1, dW2, db2, dq, dv, dk, de
 
 
