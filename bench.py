@@ -8,7 +8,7 @@ layer-direction of CogVideoX-5B (48 heads x 64, mini-batch 64, checkpoint group 
                     B = 1.  Secondary key "nc804": the same at the 9-second length (the metric's other quoted point).
   N > 1 (torchrun)  the north-star multi-GPU mode: the sequence is SHARDED over the N ranks (contiguous mini-batch ranges,
                     ttt_video_dit_b200.seq_shard.ShardedTTTMLP); the only data-path collective is the NCCL send/recv of the
-                    fp32 state {W1,b1,W2,b2} (forward) and of its gradient (backward) at the shard boundaries.  M = 4N
+                    fp32 state {W1,b1,W2,b2} (forward) and of its gradient (backward) at the shard boundaries.  M = 8N
                     independent sequences are in flight so the serial chain is full (pipeline over sequences); secondary
                     keys: single-sequence latency through the chain, and plain data-parallel replicas.
 
@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--heads", type=int, default=H_5B)
     ap.add_argument("--ckpt", type=int, default=16)
-    ap.add_argument("--seqs", type=int, default=0, help="N>1: sequences in flight through the sharded chain (default 4N)")
+    ap.add_argument("--seqs", type=int, default=0, help="N>1: sequences in flight through the sharded chain (default 8N)")
     ap.add_argument("--parallel", default="auto", choices=["auto", "seqshard", "replicas"],
                     help="N>1: sequence-sharded chain (default) or independent data-parallel replicas")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -315,6 +315,16 @@ def bench_replica(args, torch, dist, mlp_tk, world, rank, dev, mode, NC, with_e2
     return res
 
 
+_PAIRS = {}
+
+
+def _pair_groups(seq_shard):
+    """Two-rank NCCL communicators for the chain neighbours, created once per process (collective call)."""
+    if "g" not in _PAIRS:
+        _PAIRS["g"] = seq_shard.make_pair_groups()
+    return _PAIRS["g"]
+
+
 def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, steps, warmup, sampler=None):
     """The sequence-sharded chain: this rank owns mini-batch range `rank` of each of the M sequences."""
     from ttt_video_dit_b200 import seq_shard, test_time_training as tt
@@ -323,7 +333,8 @@ def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, st
     n_local = e_ - s
     ln_w, ln_b, W1, b1, W2, b2 = synth_params(torch, dev, 1, H)
     impl = seq_shard.CudaMLPRange(ln_w, ln_b, checkpoint_group_size=G)
-    stage = seq_shard.ShardedTTTMLP(impl, rank=rank, world=world)
+    pairs = _pair_groups(seq_shard)
+    stage = seq_shard.ShardedTTTMLP(impl, rank=rank, world=world, pair_groups=pairs)
     items, gouts = [], []
     for m in range(M):
         q, k, v, e, go = synth(torch, dev, 1, H, n_local, 5000 + 97 * m + rank, True)
@@ -371,7 +382,7 @@ def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, st
                 self.mb += 1
                 return r
         feed = Feed()
-        stage_e2e = seq_shard.ShardedTTTMLP(feed, rank=rank, world=world)
+        stage_e2e = seq_shard.ShardedTTTMLP(feed, rank=rank, world=world, pair_groups=pairs)
 
         def step_e2e(first=False):
             with torch.cuda.stream(s_in):
@@ -429,7 +440,7 @@ def main():
     mode = "fwd" if args.mode == "fwd" else "fwdbwd"
     H, NC, G = args.heads, args.nc, args.ckpt
     sharded = world > 1 and args.parallel in ("auto", "seqshard")
-    M = (args.seqs or 4 * world) if sharded else None
+    M = (args.seqs or 8 * world) if sharded else None
     sampler = ClockSampler(local)
     if sharded:
         r = bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, True, args.steps, args.warmup, sampler)

@@ -48,6 +48,7 @@ def _worker(rank, nproc, port, NC, direction, subgroup, ret):
     from oracle import ttt_oracle as O
     from ttt_video_dit_b200 import seq_shard
     group, members = None, list(range(nproc))
+    pairs = seq_shard.make_pair_groups() if (direction < 0 and not subgroup) else None  # one communicator per neighbour pair
     if subgroup:  # chain over global ranks [1, 2] of a 3-process job: positions 0,1 inside the group
         members = [1, 2]
         group = dist.new_group(members)
@@ -64,7 +65,8 @@ def _worker(rank, nproc, port, NC, direction, subgroup, ret):
             items.append(tuple(x.contiguous() for x in t[:4]))
             gouts.append(t[4].contiguous())
         d0 = ds[0]
-        stage = seq_shard.ShardedTTTMLP(OracleRange(O, d0["ln_w"], d0["ln_b"]), rank=pos, world=world, direction=direction, group=group)
+        stage = seq_shard.ShardedTTTMLP(OracleRange(O, d0["ln_w"], d0["ln_b"]), rank=pos, world=world, direction=direction, group=group,
+                                        pair_groups=pairs)
         outs, finals = stage.forward(items, (d0["W1"], d0["b1"], d0["W2"], d0["b2"]))
         grads, d_init, dlw, dlb = stage.backward(gouts)
         result = (pos, outs, finals, grads, d_init, dlw, dlb)

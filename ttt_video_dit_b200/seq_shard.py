@@ -146,6 +146,13 @@ def cuda_scan_fn(ln_w, ln_b, checkpoint_group_size=1 << 30):
     return fn
 
 
+def make_pair_groups(ranks=None):
+    """One two-rank process group per pair of chain neighbours (collective: every rank of the default group must call it
+    with the same ``ranks``, the global ranks of the chain in order).  Returns {frozenset({a, b}): group}."""
+    ranks = list(range(dist.get_world_size())) if ranks is None else list(ranks)
+    return {frozenset((a, b)): dist.new_group([a, b]) for a, b in zip(ranks[:-1], ranks[1:])}
+
+
 # ------------------------------------------------------------------------------------------------ training through the chain
 class CudaMLPRange:
     """Forward + backward of ONE mini-batch range of one (micro-)batch on the sm_100a kernels: the forward writes the fp32
@@ -190,20 +197,31 @@ class ShardedTTTMLP:
     ``impl`` provides forward(q,k,v,last_eta,state) -> (out, state_out, ctx) and backward(ctx, grad_out, d_state_out) ->
     (dq, dk, dv, d_eta, d_state_in, d_ln_w, d_ln_b): CudaMLPRange in the product, the oracle in the CPU gloo tests."""
 
-    def __init__(self, impl, *, rank: int, world: int, direction: int = +1, group=None):
+    def __init__(self, impl, *, rank: int, world: int, direction: int = +1, group=None, pair_groups=None):
+        """``pair_groups`` (optional): {frozenset({global_rank_a, global_rank_b}): two-rank process group} from
+        ``make_pair_groups``.  NCCL runs all point-to-point operations of ONE communicator in issue order on one stream, so on
+        a shared group a rank's send to its successor queues behind its receive from its predecessor; a communicator per
+        neighbour pair makes the two directions of a stage independent."""
         self.impl, self.group = impl, group
         self.prev, self.next = chain_neighbors(rank, world, direction, group)
+        me = dist.get_rank() if dist.is_initialized() else rank
+        pg = pair_groups or {}
+        self._pg_prev = pg.get(frozenset((me, self.prev)), group) if self.prev is not None else None
+        self._pg_next = pg.get(frozenset((me, self.next)), group) if self.next is not None else None
         self._ctx = []
         self._pending = []  # (work, buffer) of sends not yet known to be complete
 
+    def _pg(self, peer):
+        return self._pg_prev if peer == self.prev else self._pg_next
+
     def _recv_state(self, B, H, device, src):
         buf = torch.empty(B, H, STATE_NUMEL, dtype=torch.float32, device=device)
-        dist.irecv(buf, src=src, group=self.group).wait()
+        dist.irecv(buf, src=src, group=self._pg(src)).wait()
         return unpack_state(buf)
 
     def _send_state(self, state, dst):
         buf = pack_state(state)
-        self._pending.append((dist.isend(buf, dst=dst, group=self.group), buf))
+        self._pending.append((dist.isend(buf, dst=dst, group=self._pg(dst)), buf))
 
     def _drain(self):
         for w, _ in self._pending:
