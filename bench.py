@@ -340,11 +340,10 @@ def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, st
         q, k, v, e, go = synth(torch, dev, 1, H, n_local, 5000 + 97 * m + rank, True)
         items.append((q, k, v, e)); gouts.append(go)
 
-    def step():
-        outs, _ = stage.forward(items, (W1, b1, W2, b2))
+    def step():  # outputs / token gradients are dropped item by item: M sequences of results would not fit beside the inputs
+        stage.forward(items, (W1, b1, W2, b2), collect=False)
         if mode == "fwdbwd":
-            stage.backward(gouts)
-        return outs
+            stage.backward(gouts, collect=False)
     ms = timed(torch, dist, world, step, steps, warmup, sampler)
     groups = (n_local + min(G, n_local) - 1) // min(G, n_local)
     per_item = tt.LAUNCHES_FWD + ((3 * groups + (1 if rank != world - 1 else 0)) if mode == "fwdbwd" else 0)
@@ -393,9 +392,9 @@ def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, st
                         dst.copy_(src, non_blocking=True)
                     ev_in[m].record(s_in)
             feed.m = feed.mb = 0
-            stage_e2e.forward(items, (W1, b1, W2, b2))
+            stage_e2e.forward(items, (W1, b1, W2, b2), collect=False)
             if mode == "fwdbwd":
-                stage_e2e.backward(gouts)
+                stage_e2e.backward(gouts, collect=False)
             else:
                 for m in range(M):
                     ev_done[m].record(main)

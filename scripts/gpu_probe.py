@@ -73,8 +73,9 @@ for rep in range(2):
     if rep == 1:
         for ob in (0,1):
             tot = sum(t[ob*64:ob*64+14])
+            div = NC if os.environ.get('TTT_B200_PERSISTENT', '1') != '0' else G  # persistent: the slots accumulate over the whole scan
             print('   prologue cycles', t[ob*64+14], 'epilogue cycles', t[ob*64+16], flush=True)
-            print('BWD observer', ob, 'cycles/step total', tot/G, {n: round(t[ob*64+i]/G) for i,n in enumerate(bn[:14])}, flush=True)
+            print('BWD observer', ob, 'cycles/step total', tot/div, {n: round(t[ob*64+i]/div) for i,n in enumerate(bn[:14])}, flush=True)
         print('per-block K-kernel cycles (sorted):', sorted(t[128:128+48]), flush=True)
         print('smid of block b:', t[192:192+48], flush=True)
         ngr = (NC + G - 1) // G

@@ -166,14 +166,25 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem = *tmem_ptr;
 
   const size_t row_bh = (size_t)bh * p.NC * CS;  // token row of step 0 of this sequence
-  // ring addressing of the per-step recompute data (see BwdParams)
-  auto ring_of = [&](int t, int& local) { const int g = t / p.G; local = t - g * p.G; return (p.K - 1 - g) % kRingSlots; };
-  auto img_of = [&](int t) { int l; const int r = ring_of(t, l); return p.img[r] + ((size_t)bh * p.img_slots + l) * 65536; };
-  auto qt_of = [&](int t) { int l; const int r = ring_of(t, l); return p.qt[r] + ((size_t)bh * p.G + l) * 73728; };
-  auto b1img_of = [&](int t) { int l; const int r = ring_of(t, l); return p.b1img[r] + ((size_t)bh * p.img_slots + l) * HID; };
-  auto b2img_of = [&](int t) { int l; const int r = ring_of(t, l); return p.b2img[r] + ((size_t)bh * p.img_slots + l) * F; };
-  auto qb1_of = [&](int t) { int l; const int r = ring_of(t, l); return p.qb1[r] + ((size_t)bh * p.G + l) * HID; };
-  auto qb2_of = [&](int t) { int l; const int r = ring_of(t, l); return p.qb2[r] + ((size_t)bh * p.G + l) * 192; };
+  // ring addressing of the per-step recompute data (see BwdParams).  The pointers of the current step and of the next one
+  // (t - 1, whose loads are issued during step t) are kept in registers and advanced once per iteration: no divisions in
+  // the step loop.
+  struct StepIdx { int r, l; };  // ring slot and local index inside it
+  auto step_idx = [&](int t) { const int g = t / p.G; return StepIdx{(p.K - 1 - g) % kRingSlots, t - g * p.G}; };
+  auto step_back = [&](StepIdx& si) {  // index of the step before the one si points at
+    // crossing into the previous checkpoint group = the next unit: next ring slot, last local index (every group below the
+    // last one is full)
+    if (si.l == 0) { si.r = (si.r + 1) % kRingSlots; si.l = p.G - 1; }
+    else --si.l;
+  };
+  auto img_at = [&](StepIdx si) { return p.img[si.r] + ((size_t)bh * p.img_slots + si.l) * 65536; };
+  auto qt_at = [&](StepIdx si) { return p.qt[si.r] + ((size_t)bh * p.G + si.l) * 73728; };
+  auto b1_at = [&](StepIdx si) { return p.b1img[si.r] + ((size_t)bh * p.img_slots + si.l) * HID; };
+  auto b2_at = [&](StepIdx si) { return p.b2img[si.r] + ((size_t)bh * p.img_slots + si.l) * F; };
+  auto q1_at = [&](StepIdx si) { return p.qb1[si.r] + ((size_t)bh * p.G + si.l) * HID; };
+  auto q2_at = [&](StepIdx si) { return p.qb2[si.r] + ((size_t)bh * p.G + si.l) * 192; };
+  StepIdx cur = step_idx(p.t_hi), nxt = cur;  // nxt: step t - 1 (valid while t > t_lo)
+  if (p.t_hi > p.t_lo) step_back(nxt);
   // persistent mode: before the first access to the buffers of the unit that holds step t
   auto wait_unit_of = [&](int t) {
     if (p.ready == nullptr) return;
@@ -181,18 +192,18 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int steps = min(p.NC, (g + 1) * p.G) - g * p.G;
     wait_counter(p.ready + (size_t)u * gridDim.x + bh, (unsigned)steps);
   };
-
   // slot roles (byte offsets of the four 32 KB hidden-lane slots); they rotate every iteration
   uint32_t sW1 = SM_HS, sA = SM_HS + 32768, sB = SM_HS + 65536, sC = SM_HS + 98304;
   uint32_t mma_phase = 0, ph_kv = 0, ph_qd = 0, ph_w1 = 0, ph_w1r = 0, ph_w2 = 0, ph_x2 = 0, ph_aux = 0, ph_xb = 0;
 
   // Loads that feed iteration t: Q_t tile + the Q-side factor tiles of step t.  Thread 0 only.
+  int tcur = p.t_hi;  // the step `cur` points at (load helpers take t = tcur or tcur - 1)
   auto load_xb = [&](int t, uint32_t xs) {  // Xbar2^T factor tile of step t
     mbar_expect_tx(bar_xb, 32768);
-    bulk_load_1d(smem + xs, qt_of(t), 32768, bar_xb);
+    bulk_load_1d(smem + xs, qt_at(t == tcur ? cur : nxt), 32768, bar_xb);
   };
   auto load_q_rest = [&](int t, uint32_t zs) {  // Q_t tile, dZbar1^T -> slot zs, dZbar2 -> TT0
-    const uint8_t* src = qt_of(t);
+    const uint8_t* src = qt_at(t == tcur ? cur : nxt);
     mbar_expect_tx(bar_qd, 8192 + 32768 + 8192);
     tma_load_2d(smem + SM_TQ, &tmQ, 0, (int)(row_bh + (size_t)t * CS), bar_qd);
     bulk_load_1d(smem + zs, src + 32768, 32768, bar_qd);
@@ -202,7 +213,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   wait_unit_of(p.t_hi);
   if (warp_u == 0 && elect_one()) {
     const int t = p.t_hi;
-    const uint8_t* im = img_of(t);
+    const uint8_t* im = img_at(cur);
     mbar_expect_tx(bar_w1, 32768);
     bulk_load_1d(smem + sW1, im, 32768, bar_w1);
     mbar_expect_tx(bar_w2, 32768);
@@ -243,12 +254,12 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   uint32_t g1p[32], g2p[32];  // packed bf16: gelu'(Z1) (later gelu'(Zbar1)), gelu''(Z1) (later term2)
 
-  float nb1 = b1img_of(p.t_hi)[j], nb2 = 0.f;
-  float nq1 = qb1_of(p.t_hi)[j], nq2 = 0.f, nqg = 0.f, nqb = 0.f;
+  float nb1 = b1_at(cur)[j], nb2 = 0.f;
+  float nq1 = q1_at(cur)[j], nq2 = 0.f, nqg = 0.f, nqb = 0.f;
   unsigned short neta = 0;
   if (tid < 64) {
-    nb2 = b2img_of(p.t_hi)[tid];
-    const float* q2 = qb2_of(p.t_hi);
+    nb2 = b2_at(cur)[tid];
+    const float* q2 = q2_at(cur);
     nq2 = q2[tid]; nqg = q2[64 + tid]; nqb = q2[128 + tid];
     if (p.t_hi < p.NC) neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)p.t_hi * CS + tid];
   }
@@ -270,11 +281,11 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     db1r += q1t;         // ... and to d b1
     if (t > p.t_lo) {  // prefetch for iteration t-1
       if (t % p.G == 0) wait_unit_of(t - 1);  // step t-1 opens the next unit (persistent mode): its recompute must be complete
-      nb1 = b1img_of(t - 1)[j];
-      nq1 = qb1_of(t - 1)[j];
+      nb1 = b1_at(nxt)[j];
+      nq1 = q1_at(nxt)[j];
       if (tid < 64) {
-        nb2 = b2img_of(t - 1)[tid];
-        const float* q2 = qb2_of(t - 1);
+        nb2 = b2_at(nxt)[tid];
+        const float* q2 = q2_at(nxt);
         nq2 = q2[tid]; nqg = q2[64 + tid]; nqb = q2[128 + tid];
         neta = reinterpret_cast<const unsigned short*>(p.last_eta)[row_bh + (size_t)(t - 1) * CS + tid];
       }
@@ -476,7 +487,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (warp_u == 0 && elect_one()) {  // sA (CW1) and sC (G1eta) are free: reload the W1 image and the X2 tile
         bulk_wait<0>();
         mbar_expect_tx(bar_w1r, 32768);
-        bulk_load_1d(smem + sA, img_of(t), 32768, bar_w1r);
+        bulk_load_1d(smem + sA, img_at(cur), 32768, bar_w1r);
         mbar_expect_tx(bar_x2, 32768);
         bulk_load_1d(smem + sC, p.x2spill + (size_t)bh * 32768, 32768, bar_x2);
       }
@@ -559,9 +570,9 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if ((lane & 1) == 0) {
           const int f = c0 + (lane >> 1);
           const bool hi = (warp & 1) != 0;  // token rows 32-63: the other accumulator set (one writer per word)
-          (hi ? db2h : db2c)[f] += dg[0];
-          (hi ? dgam2 : dgam)[f] += cg[0];
-          (hi ? dbet2 : dbet)[f] += dy[0];
+          atomicAdd(&(hi ? db2h : db2c)[f], dg[0]);  // fire-and-forget shared-memory adds; each word has ONE writer per step
+          atomicAdd(&(hi ? dgam2 : dgam)[f], cg[0]);
+          atomicAdd(&(hi ? dbet2 : dbet)[f], dy[0]);
         }
       }
       PHASE_SYNC();
@@ -583,7 +594,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       TICK(10);
       if (warp_u == 0 && (t > p.t_lo) && elect_one()) {  // the W2 image buffer is free now: fetch the next one
         mbar_expect_tx(bar_w2, 32768);
-        bulk_load_1d(smem + SM_W2I, img_of(t - 1) + 32768, 32768, bar_w2);
+        bulk_load_1d(smem + SM_W2I, img_at(nxt) + 32768, 32768, bar_w2);
       }
       // ===== A10 [H]: dZ1 = dX2 * gelu'(Z1) + term2 -> sB ; d b1 += sum dZ1
       {
@@ -609,7 +620,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_aux, ph_aux); ph_aux ^= 1;   // DG1 (sW1) and X2 (sC) are no longer read by any MMA
       if (warp_u == 0 && (t > p.t_lo) && elect_one()) {
         mbar_expect_tx(bar_w1, 32768);
-        bulk_load_1d(smem + sC, img_of(t - 1), 32768, bar_w1);
+        bulk_load_1d(smem + sC, img_at(nxt), 32768, bar_w1);
         load_xb(t - 1, sW1);
       }
       PHASE_SYNC();
@@ -656,6 +667,10 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t n0 = sC, n1 = sW1, n2 = sA, n3 = sB;
       sW1 = n0; sA = n1; sB = n2; sC = n3;
     }
+    // advance the step pointers: cur <- step t - 1, nxt <- step t - 2
+    cur = nxt;
+    tcur = t - 1;
+    if (t - 1 > p.t_lo) step_back(nxt);
   }
 
   TICK(15);  // (loop tail)

@@ -228,10 +228,11 @@ class ShardedTTTMLP:
             w.wait()
         self._pending = []
 
-    def forward(self, items, init_state):
+    def forward(self, items, init_state, collect=True):
         """items: list of (q, k, v, last_eta) local ranges [B,H,NC_local,CS,F] / [B,H,NC_local,CS]; init_state: (W1,b1,W2,b2)
         [B,H,...], read by the first rank of the chain only.  Returns (outs, final_states or None): final_states (one per
-        item) only on the last rank of the chain."""
+        item) only on the last rank of the chain.  ``collect=False`` drops each item's output as soon as it is produced
+        (benchmarks; a caller that consumes outputs item by item)."""
         outs, finals = [], []
         self._ctx = []
         for q, k, v, le in items:
@@ -239,7 +240,9 @@ class ShardedTTTMLP:
             st = tuple(t.contiguous() for t in init_state) if self.prev is None else self._recv_state(B, H, q.device, self.prev)
             out, st_out, ctx = self.impl.forward(q, k, v, le, st)
             self._ctx.append(ctx)
-            outs.append(out)
+            if collect:
+                outs.append(out)
+            del out
             if self.next is not None:
                 self._send_state(st_out, self.next)
             else:
@@ -247,7 +250,7 @@ class ShardedTTTMLP:
         self._drain()
         return outs, (finals if self.next is None else None)
 
-    def backward(self, grad_outs, d_final_states=None):
+    def backward(self, grad_outs, d_final_states=None, collect=True):
         """grad_outs: one upstream gradient per item (layout of the outputs).  d_final_states: optional per-item upstream
         gradient of the final state, last rank of the chain only (zero at the reference's op boundary).  Returns
         (item_grads = [(dq, dk, dv, d_last_eta)], d_init_state or None, d_ln_w, d_ln_b): d_init_state (summed over items: the
@@ -262,7 +265,9 @@ class ShardedTTTMLP:
                 d_out_state = None if d_final_states is None else d_final_states[m]
             dq, dk, dv, de, d_in, a, b = self.impl.backward(self._ctx[m], go, d_out_state)
             self._ctx[m] = None
-            item_grads.append((dq, dk, dv, de))
+            if collect:  # collect=False: the token gradients of an item are dropped once its state gradient is on its way
+                item_grads.append((dq, dk, dv, de))
+            del dq, dk, dv, de
             dlw = a if dlw is None else dlw + a
             dlb = b if dlb is None else dlb + b
             if self.prev is not None:
