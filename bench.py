@@ -415,6 +415,77 @@ def bench_sharded(args, torch, dist, world, rank, dev, mode, NC, M, with_e2e, st
     return res
 
 
+def synth_layer_params(torch, dev, E, H, TE=512, seed=7):
+    """Random-init TransformerLayer state_dict with the reference's names and init scales (dit.py:281-320, ttt_layer.py:404-416),
+    GEMM weights in bf16, norm / TTT-state parameters in fp32."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, device=dev)
+    bf = torch.bfloat16
+    P = {}
+    lin = lambda name, o, i: P.update({f"{name}.weight": (rn(o, i) / i ** 0.5).to(bf), f"{name}.bias": torch.zeros(o, device=dev, dtype=bf)})
+    for n in ("pre_seq_adaLN_modulation.1", "pre_mlp_adaLN_modulation.1"):
+        lin(n, 6 * E, TE)
+    for n in ("pre_seq_layernorm", "pre_mlp_layernorm"):
+        P[f"{n}.weight"], P[f"{n}.bias"] = torch.ones(E, device=dev), torch.zeros(E, device=dev)
+    sb = "seq_modeling_block."
+    for n in ("q", "k", "v", "o"):
+        lin(sb + n, E, E)
+    for n in ("q_norm", "k_norm"):
+        P[sb + n + ".weight"], P[sb + n + ".bias"] = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    for n in ("forward_ssm_gating_video", "forward_ssm_gating_text", "backward_ssm_gating_video", "backward_ssm_gating_text"):
+        P[sb + n + ".gating_alpha"] = torch.full((E,), 0.1, device=dev)
+    t = sb + "ssm.ttt."
+    for n in ("wq", "wk", "wv", "wo"):
+        lin(t + n, E, E)
+    P[t + "learnable_ttt_lr_weight"] = (0.02 * rn(H, 1, E)).to(bf); P[t + "learnable_ttt_lr_bias"] = torch.zeros(H, 1, device=dev, dtype=bf)
+    P[t + "ttt_norm_weight"], P[t + "ttt_norm_bias"] = torch.ones(H, 64, device=dev), torch.zeros(H, 64, device=dev)
+    P[t + "post_norm.weight"], P[t + "post_norm.bias"] = torch.ones(E, device=dev), torch.zeros(E, device=dev)
+    P[t + "W1"], P[t + "b1"] = 0.02 * rn(H, 64, 256), torch.zeros(H, 1, 256, device=dev)
+    P[t + "W2"], P[t + "b2"] = 0.02 * rn(H, 256, 64), torch.zeros(H, 1, 64, device=dev)
+    lin("mlp.layer1", 4 * E, E); lin("mlp.layer2", E, 4 * E)
+    return P
+
+
+def bench_dit_layer(torch, dev, steps=3, warmup=2):
+    """Secondary key: ONE whole CogVideoX-5B TransformerLayer (adaLN shell, local attention, forward + reversed gated TTT-MLP,
+    token MLP; all Linears) forward + backward at the 3-second length, B = 1 -- the "DiT+TTT" of BASELINE.json's metric at
+    layer granularity (the 5B model is 42 such layers).  Measured twice: attention on this repo's kernel, and on the library
+    SDPA the reference calls."""
+    from ttt_video_dit_b200 import transformer_layer as TL
+    E, H, TLen, frames = 3072, 48, 498, 13
+    out = {}
+    P = {k: v.requires_grad_(True) for k, v in synth_layer_params(torch, dev, E, H).items()}
+    L = TLen + frames * 30 * 45
+    g = torch.Generator(device=dev).manual_seed(3)
+    emb = torch.randn(1, L, E, generator=g, device=dev).to(torch.bfloat16).requires_grad_(True)
+    t_emb = torch.randn(1, 512, generator=g, device=dev).to(torch.bfloat16)
+    go = torch.randn(1, L, E, generator=g, device=dev).to(torch.bfloat16)
+    for impl in ("b200", "library"):
+        meta = TL.LayerMeta(num_heads=H, text_length=TLen, num_chunks=1, num_frames=frames, latent_height=30, latent_width=45,
+                            attention_impl=impl)
+
+        def step():
+            y = TL.transformer_layer_forward(emb, t_emb, P, meta)
+            y.backward(go)
+            emb.grad = None
+            for v in P.values():
+                v.grad = None
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[f"attention_{impl}"] = {"ms_per_layer": ms, "tokens_per_s_per_layer": L / (ms * 1e-3), "model_tokens_per_s_42_layers": L / (42 * ms * 1e-3)}
+    out["note"] = (f"one TransformerLayer fwd+bwd, CogVideoX-5B dims (E={E}, {H} heads), 3-sec video (L={L} tokens), B=1, bf16 GEMMs by cuBLAS; "
+                   "attention_b200 = csrc/attn_*.cu, attention_library = F.scaled_dot_product_attention as in the reference")
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -465,6 +536,9 @@ def main():
             r9 = bench_replica(args, torch, dist, mlp_tk, world, rank, dev, mode, NC_9S, False, 5, 2)
             secondary["nc804"] = {"ms_per_step": r9["ms_per_step"], "tokens_per_s": r9["tokens_per_step"] / (r9["ms_per_step"] * 1e-3),
                                   "note": "the 9-second video (3 interleaved segments, NC = 804), same op and mode"}
+            if mode == "fwdbwd" and H == H_5B:
+                torch.cuda.empty_cache()
+                secondary["dit_layer"] = bench_dit_layer(torch, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -437,6 +437,13 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_ss(tmem + TM_W2 + 64 * h, desc_advance(da, 32 * k), desc_advance(dg_mn, 2048 * k), IDESC_U2, 1);
       }
     }
+    if (kF16) {  // in the shadow of the D3 batch: next iteration's token tiles (TMA issued at the top of this iteration) bf16 ->
+                 // f16 in place; the proxy fences + barriers of P6 / P8 order these writes before the D1 issue that reads them
+      const int ns = slot ^ 1;
+      mbar_wait(&tma_bar[ns], ((it + 1) >> 1) & 1);
+      if (it + 1 < NC) tile_bf16_to_f16(sbase + SM_KQ + ns * 16384, tid);  // K_{it+1}
+      tile_bf16_to_f16(sbase + SM_KQ + ns * 16384 + 8192, tid);             // Q_{it}
+    }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
@@ -505,12 +512,6 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         store_row_op<kF16>(sbase + SM_W1B, j, 4 * c, v);
         if (ck) store_w1_col(p.W1c + kidx * F * HID, j, v, 32 * c);
         if (fin) store_w1_col(p.W1o + (size_t)bh * F * HID, j, v, 32 * c);
-      }
-      if (kF16) {  // next iteration's token tiles (TMA issued at the top of this iteration): bf16 -> f16 in place
-        const int ns = slot ^ 1;
-        mbar_wait(&tma_bar[ns], ((it + 1) >> 1) & 1);
-        if (nstep < NC) tile_bf16_to_f16(sbase + SM_KQ + ns * 16384, tid);  // K_{it+1}
-        tile_bf16_to_f16(sbase + SM_KQ + ns * 16384 + 8192, tid);            // Q_{it}
       }
       // W1b is complete: start the next iteration's D1 now, it runs under the W2 conversion below
       fence_proxy_async();

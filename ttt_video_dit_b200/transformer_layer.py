@@ -111,6 +111,7 @@ class LayerMeta:
     prefix_temporal_length: int = 1
     layer_norm_eps: float = 1e-6
     theta: float = 10000.0
+    attention_impl: str = "b200"   # "library": the library SDPA the reference calls, see attention.local_attention
     tables: dict = field(default_factory=dict, repr=False)
 
     @property
@@ -158,7 +159,8 @@ def seq_modeling_block_forward(emb, P, meta: LayerMeta):
     Lt = meta.seq_text_length
     text, vid = emb[:, :Lt], emb[:, Lt:]
     y = attention.local_attention(vid, text, P, meta.num_heads, meta.text_length, meta.tokens_per_frame, meta.num_chunks,
-                                  meta.attn_length, meta.prefix_temporal_length, t["attn_sin"], t["attn_cos"], meta.layer_norm_eps)
+                                  meta.attn_length, meta.prefix_temporal_length, t["attn_sin"], t["attn_cos"], meta.layer_norm_eps,
+                                  impl=meta.attention_impl)
     Pt = _sub(P, "ssm.ttt.")
 
     def ssm(x):
