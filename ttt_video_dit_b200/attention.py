@@ -106,8 +106,8 @@ def local_attention(vid, text, P, num_heads, text_length, tokens_per_frame, num_
         q = F.linear(cur, P["q.weight"], P["q.bias"]).reshape(B, T, num_heads, D)
         k = F.linear(cur, P["k.weight"], P["k.bias"]).reshape(B, T, num_heads, D)
         v = F.linear(cur, P["v.weight"], P["v.bias"]).reshape(B, T, num_heads, D)
-        q = F.layer_norm(q, (D,), P["q_norm.weight"], P["q_norm.bias"], ln_eps)
-        k = F.layer_norm(k, (D,), P["k_norm.weight"], P["k_norm.bias"], ln_eps)
+        q = F.layer_norm(q, (D,), P["q_norm.weight"].to(q.dtype), P["q_norm.bias"].to(q.dtype), ln_eps)
+        k = F.layer_norm(k, (D,), P["k_norm.weight"].to(k.dtype), P["k_norm.bias"].to(k.dtype), ln_eps)
         Lv = T - text_length
         c, sn = cos[:Lv].to(q.dtype)[None, :, None, :], sin[:Lv].to(q.dtype)[None, :, None, :]
         q = torch.cat([q[:, :text_length], q[:, text_length:] * c + _rotate_half(q[:, text_length:]) * sn], dim=1)
