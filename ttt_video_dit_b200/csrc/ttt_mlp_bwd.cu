@@ -600,19 +600,20 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
         float acc = 0.f;
+        float v[2][32];
+        tmem_ld32(src, reinterpret_cast<uint32_t*>(v[0]));
+        tmem_ld32(src + 32, reinterpret_cast<uint32_t*>(v[1]));
+        tc_wait_ld();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
-          tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint32_t gp1 = g1p[16 * c + i / 2], tp = g2p[16 * c + i / 2];
-            v[i] = fmaf(v[i], bf16_lo(gp1), bf16_lo(tp));
-            v[i + 1] = fmaf(v[i + 1], bf16_hi(gp1), bf16_hi(tp));
-            acc += v[i] + v[i + 1];
+            v[c][i] = fmaf(v[c][i], bf16_lo(gp1), bf16_lo(tp));
+            v[c][i + 1] = fmaf(v[c][i + 1], bf16_hi(gp1), bf16_hi(tp));
+            acc += v[c][i] + v[c][i + 1];
           }
-          st_row32(sbase + sB, j, 4 * c, v);
+          st_row32(sbase + sB, j, 4 * c, v[c]);
         }
         db1r += acc;
       }
