@@ -160,6 +160,20 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                            const float* alpha_video, void* dres, void* ds, float* d_alpha_text, float* d_alpha_video,
                            int B, int L, int E, int text_len, int num_chunks, int perm_s, void* stream);
 
+/* Prologue of the local attention: per-head LayerNorm of q and k + 3-D rotary embedding of the video tokens with segment-local
+ * positions, one pass.  Replaces self.q_norm / self.k_norm / self.rotary at ttt/models/cogvideo/dit.py:188-194 (nn.LayerNorm(64,
+ * eps), cogvideo/utils.py:93-99,432-437).  q/k/q_out/k_out bf16 [B,T,H,64] (layout of the q / k Linear outputs), tokens
+ * t < text_len are text (not rotated), token t >= text_len uses table row t - text_len; norm_weight / norm_bias f32 [2,64]
+ * (q_norm then k_norm); rope_cos / rope_sin f32 [>= T - text_len, 64] with every angle repeated over its feature pair.
+ * _backward: dq_out/dk_out -> dq/dk (bf16), d_norm_weight / d_norm_bias f32 [2,64] (overwritten). */
+int ttt_b200_qk_norm_rope(const void* q, const void* k, const float* norm_weight, const float* norm_bias, const float* rope_cos,
+                          const float* rope_sin, void* q_out, void* k_out, int B, int T, int H, int text_len, float eps,
+                          void* stream);
+int ttt_b200_qk_norm_rope_backward(const void* q, const void* k, const float* norm_weight, const float* rope_cos,
+                                   const float* rope_sin, const void* dq_out, const void* dk_out, void* dq, void* dk,
+                                   float* d_norm_weight, float* d_norm_bias, int B, int T, int H, int text_len, float eps,
+                                   void* stream);
+
 /* adaLN shell of the DiT TransformerLayer around the hot path (ttt/models/cogvideo/dit.py:321-382).
  * ln_affine: out[b,l,:] = LayerNorm_noaffine(x[b,l,:]; eps) * A[b,s,:] + C[b,s,:], s = (l < text_len ? 0 : 1) -- replaces
  * pre_seq_layernorm / pre_mlp_layernorm + modulate(x, shift, scale) (dit.py:344-345,367-368) with the caller folding

@@ -33,6 +33,8 @@ def test_every_public_op_refuses_host_tensors():
         "output_norm": lambda: process_input.output_norm(bf(torch.randn(1, 2, 2, 64, 64)), torch.ones(128), torch.zeros(128)),
         "ssm_forward": lambda: seq_block.ssm_forward(x, lambda t: t, 0, 1, False, gate, gate, gate, gate),
         "LnAffine": lambda: transformer_layer.LnAffine.apply(x, torch.ones(1, 2, 128), torch.zeros(1, 2, 128), 0, 1e-6),
+        "QKNormRope": lambda: attention.QKNormRope.apply(q, q, torch.ones(64), torch.zeros(64), torch.ones(64), torch.zeros(64),
+                                                         torch.zeros(128, 64), torch.ones(128, 64), 0, 1e-6),
         "GateAdd": lambda: transformer_layer.GateAdd.apply(x, x, torch.ones(1, 2, 128), 0),
     }
     for name, fn in calls.items():

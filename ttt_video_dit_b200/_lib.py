@@ -31,6 +31,9 @@ _SIGS = {
     "ttt_b200_output_norm_backward": ([_vp, _fp, _vp, _vp, _vp, _fp, _fp] + [_i] * 3 + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_gate_forward": ([_vp, _vp, _fp, _fp, _vp, _vp] + [_i] * 6 + [_vp], ctypes.c_int),
     "ttt_b200_gate_backward": ([_vp, _vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 6 + [_vp], ctypes.c_int),
+    "ttt_b200_qk_norm_rope": ([_vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp] + [_i] * 4 + [ctypes.c_float, _vp], ctypes.c_int),
+    "ttt_b200_qk_norm_rope_backward": ([_vp, _vp, _fp, _fp, _fp, _vp, _vp, _vp, _vp, _fp, _fp] + [_i] * 4 + [ctypes.c_float, _vp],
+                                       ctypes.c_int),
     "ttt_b200_ln_affine": ([_vp, _fp, _fp, _vp] + [_i] * 4 + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_ln_affine_backward": ([_vp, _fp, _vp, _vp, _fp, _fp] + [_i] * 4 + [ctypes.c_float, _vp], ctypes.c_int),
     "ttt_b200_gate_add": ([_vp, _vp, _fp, _vp] + [_i] * 4 + [_vp], ctypes.c_int),

@@ -68,10 +68,43 @@ def sdpa_bthd(q, k, v, scale=None):
     return out
 
 
-def _rotate_half(x):
-    x = x.reshape(*x.shape[:-1], -1, 2)
-    x1, x2 = x.unbind(-1)
-    return torch.stack((-x2, x1), dim=-1).flatten(-2)
+class QKNormRope(torch.autograd.Function):
+    """Fused attention prologue (csrc/attn_prologue.cu): per-head LayerNorm of q and k + RoPE on the video rows, one pass
+    forward and one backward.  q, k: bf16 [B, T, H, 64]; weights / biases of q_norm and k_norm ([64] each); sin / cos tables
+    [>= T - text_len, 64]."""
+
+    @staticmethod
+    def forward(ctx, q, k, qw, qb, kw, kb, sin, cos, text_len, eps):
+        B, T, H, D = _check_qkv(q, k, k)
+        f32 = lambda t: t.detach().to(device=q.device, dtype=torch.float32)
+        gamma = torch.stack((f32(qw), f32(kw))).contiguous()
+        beta = torch.stack((f32(qb), f32(kb))).contiguous()
+        c, s = f32(cos).contiguous(), f32(sin).contiguous()
+        if c.shape[0] < T - text_len or c.shape[-1] != 64:
+            raise RuntimeError("QKNormRope: RoPE tables must be [>= video tokens of the segment, 64]")
+        qo, ko = torch.empty_like(q), torch.empty_like(k)
+        p = _lib.ptr
+        code = _lib.lib().ttt_b200_qk_norm_rope(p(q), p(k), p(gamma), p(beta), p(c), p(s), p(qo), p(ko), B, T, H, int(text_len),
+                                                float(eps), _lib.current_stream(q))
+        _lib.check(code, "ttt_b200_qk_norm_rope")
+        ctx.save_for_backward(q, k, gamma, c, s)
+        ctx.meta = (int(text_len), float(eps), qw.dtype, qb.dtype, kw.dtype, kb.dtype)
+        return qo, ko
+
+    @staticmethod
+    def backward(ctx, dqo, dko):
+        q, k, gamma, c, s = ctx.saved_tensors
+        text_len, eps, dt_qw, dt_qb, dt_kw, dt_kb = ctx.meta
+        B, T, H, D = q.shape
+        dqo, dko = dqo.to(torch.bfloat16).contiguous(), dko.to(torch.bfloat16).contiguous()
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        dg = torch.empty(2, 64, device=q.device, dtype=torch.float32)
+        db = torch.empty_like(dg)
+        p = _lib.ptr
+        code = _lib.lib().ttt_b200_qk_norm_rope_backward(p(q), p(k), p(gamma), p(c), p(s), p(dqo), p(dko), p(dq), p(dk), p(dg), p(db),
+                                                         B, T, H, text_len, eps, _lib.current_stream(q))
+        _lib.check(code, "ttt_b200_qk_norm_rope_backward")
+        return dq, dk, dg[0].to(dt_qw), db[0].to(dt_qb), dg[1].to(dt_kw), db[1].to(dt_kb), None, None, None, None
 
 
 def _sdpa_library(q, k, v):
@@ -106,12 +139,9 @@ def local_attention(vid, text, P, num_heads, text_length, tokens_per_frame, num_
         q = F.linear(cur, P["q.weight"], P["q.bias"]).reshape(B, T, num_heads, D)
         k = F.linear(cur, P["k.weight"], P["k.bias"]).reshape(B, T, num_heads, D)
         v = F.linear(cur, P["v.weight"], P["v.bias"]).reshape(B, T, num_heads, D)
-        q = F.layer_norm(q, (D,), P["q_norm.weight"].to(q.dtype), P["q_norm.bias"].to(q.dtype), ln_eps)
-        k = F.layer_norm(k, (D,), P["k_norm.weight"].to(k.dtype), P["k_norm.bias"].to(k.dtype), ln_eps)
-        Lv = T - text_length
-        c, sn = cos[:Lv].to(q.dtype)[None, :, None, :], sin[:Lv].to(q.dtype)[None, :, None, :]
-        q = torch.cat([q[:, :text_length], q[:, text_length:] * c + _rotate_half(q[:, text_length:]) * sn], dim=1)
-        k = torch.cat([k[:, :text_length], k[:, text_length:] * c + _rotate_half(k[:, text_length:]) * sn], dim=1)
+        # q/k LayerNorm + segment-local RoPE (dit.py:188-194): one fused pass instead of ~10 elementwise ops per tensor
+        q, k = QKNormRope.apply(q.contiguous(), k.contiguous(), P["q_norm.weight"], P["q_norm.bias"], P["k_norm.weight"],
+                                P["k_norm.bias"], sin, cos, text_length, ln_eps)
         core = sdpa_bthd if impl == "b200" else _sdpa_library
         a = core(q.contiguous(), k.contiguous(), v.contiguous()).reshape(B, T, E)
         a = F.linear(a, P["o.weight"], P["o.bias"])

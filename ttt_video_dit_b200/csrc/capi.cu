@@ -201,6 +201,29 @@ int ttt_b200_gate_backward(const void* dout, const void* drev, const void* s, co
                   "ttt_b200_gate_backward");
 }
 
+int ttt_b200_qk_norm_rope(const void* q, const void* k, const float* norm_weight, const float* norm_bias, const float* rope_cos,
+                          const float* rope_sin, void* q_out, void* k_out, int B, int T, int H, int text_len, float eps,
+                          void* stream) {
+  if (!q || !k || !norm_weight || !norm_bias || !rope_cos || !rope_sin || !q_out || !k_out)
+    return fail(-1, "ttt_b200_qk_norm_rope: null pointer argument");
+  TB_BIND_DEVICE(q);
+  return cuda_ret(tb::launch_qk_norm_rope(q, k, norm_weight, norm_bias, rope_cos, rope_sin, q_out, k_out, B, T, H, text_len, eps,
+                                          (cudaStream_t)stream),
+                  "ttt_b200_qk_norm_rope");
+}
+
+int ttt_b200_qk_norm_rope_backward(const void* q, const void* k, const float* norm_weight, const float* rope_cos,
+                                   const float* rope_sin, const void* dq_out, const void* dk_out, void* dq, void* dk,
+                                   float* d_norm_weight, float* d_norm_bias, int B, int T, int H, int text_len, float eps,
+                                   void* stream) {
+  if (!q || !k || !norm_weight || !rope_cos || !rope_sin || !dq_out || !dk_out || !dq || !dk || !d_norm_weight || !d_norm_bias)
+    return fail(-1, "ttt_b200_qk_norm_rope_backward: null pointer argument");
+  TB_BIND_DEVICE(q);
+  return cuda_ret(tb::launch_qk_norm_rope_backward(q, k, norm_weight, rope_cos, rope_sin, dq_out, dk_out, dq, dk, d_norm_weight,
+                                                   d_norm_bias, B, T, H, text_len, eps, (cudaStream_t)stream),
+                  "ttt_b200_qk_norm_rope_backward");
+}
+
 int ttt_b200_ln_affine(const void* x, const float* A, const float* C, void* out, int B, int L, int E, int text_len, float eps,
                        void* stream) {
   if (!x || !A || !C || !out) return fail(-1, "ttt_b200_ln_affine: null pointer argument");

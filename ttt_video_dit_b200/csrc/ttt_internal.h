@@ -152,3 +152,12 @@ cudaError_t launch_gate_add_backward(const void* gout, const void* y, const floa
 namespace tb {
 cudaError_t launch_dsmem_probe(int mode, int bytes, int iters, float* out, cudaStream_t stream);
 }  // namespace tb
+
+namespace tb {
+cudaError_t launch_qk_norm_rope(const void* q, const void* k, const float* gamma, const float* beta, const float* cosT,
+                                const float* sinT, void* q_out, void* k_out, int B, int T, int H, int text_len, float eps,
+                                cudaStream_t stream);
+cudaError_t launch_qk_norm_rope_backward(const void* q, const void* k, const float* gamma, const float* cosT, const float* sinT,
+                                         const void* dq_out, const void* dk_out, void* dq, void* dk, float* dgamma, float* dbeta,
+                                         int B, int T, int H, int text_len, float eps, cudaStream_t stream);
+}  // namespace tb
