@@ -51,7 +51,12 @@ qk_norm_rope_fwd_kernel(const uint4* __restrict__ q, const uint4* __restrict__ k
   float g[8], bt[8];
   load8f(gamma + which * 64 + 8 * piece, g);
   load8f(beta + which * 64 + 8 * piece, bt);
-  for (long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); row < rows; row += (long long)gridDim.x * 32) {
+  // the row statistics use full-mask warp shuffles: every lane of a warp must run the same number of iterations, so the loop
+  // bound is per CTA (32 rows at a time) and rows past the end are computed on a clamped index and not stored
+  for (long long row0 = (long long)blockIdx.x * 32; row0 < rows; row0 += (long long)gridDim.x * 32) {
+    const long long rr = row0 + (threadIdx.x >> 3);
+    const bool valid = rr < rows;
+    const long long row = valid ? rr : rows - 1;
     const int t = (int)((row / H) % T);
     float v[8];
     unpack8p(x[row * 8 + piece], v);
@@ -76,7 +81,7 @@ qk_norm_rope_fwd_kernel(const uint4* __restrict__ q, const uint4* __restrict__ k
         v[e + 1] = b * c[e + 1] + a * sn[e + 1];
       }
     }
-    y[row * 8 + piece] = pack8p(v);
+    if (valid) y[row * 8 + piece] = pack8p(v);
   }
 }
 
@@ -97,11 +102,18 @@ qk_norm_rope_bwd_kernel(const uint4* __restrict__ q, const uint4* __restrict__ k
   for (int e = 0; e < 8; ++e) { dg[e] = 0.f; db[e] = 0.f; }
   if (threadIdx.x < 128) (&acc[0][0])[threadIdx.x] = 0.f;
   __syncthreads();
-  for (long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); row < rows; row += (long long)gridDim.x * 32) {
+  for (long long row0 = (long long)blockIdx.x * 32; row0 < rows; row0 += (long long)gridDim.x * 32) {  // warp-uniform trip count
+    const long long rr = row0 + (threadIdx.x >> 3);
+    const bool valid = rr < rows;
+    const long long row = valid ? rr : rows - 1;
     const int t = (int)((row / H) % T);
     float v[8], d[8];
     unpack8p(x[row * 8 + piece], v);
     unpack8p(dy[row * 8 + piece], d);
+    if (!valid) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = 0.f;  // contributes nothing to the parameter gradients
+    }
     if (t >= text_len) {  // transposed rotation: d y from d out
       float c[8], sn[8];
       load8f(cosT + (size_t)(t - text_len) * 64 + 8 * piece, c);
@@ -134,7 +146,7 @@ qk_norm_rope_bwd_kernel(const uint4* __restrict__ q, const uint4* __restrict__ k
     const float m1 = sum8(s1) * (1.f / 64.f), m2 = sum8(s2) * (1.f / 64.f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = rstd * (d[e] - m1 - v[e] * m2);
-    dx[row * 8 + piece] = pack8p(d);
+    if (valid) dx[row * 8 + piece] = pack8p(d);
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
