@@ -71,7 +71,7 @@ def test_qk_norm_rope_prologue(B, T, H, text_len):
     eps = 1e-6
 
     def rot(x):
-        x = x.reshape(*x.shape[:-1], -1, 2)
+        x = x.reshape(*x.shape[:-1], 32, 2)
         a, b = x.unbind(-1)
         return torch.stack((-b, a), dim=-1).flatten(-2)
 
