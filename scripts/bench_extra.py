@@ -159,8 +159,77 @@ def bench_block(frames=13, H=48, B=1, TL=498):
                       "shape": [B, L, E], "ms": ms, "tokens_per_s": B * L / ms * 1e3}))
 
 
+def bench_adaln(L=18048, E=3072, B=1):
+    """adaLN shell kernels (csrc/adaln.cu) forward and backward vs the HBM roofline: ln_affine reads x and writes out (4 bytes
+    per element), its backward reads x, g and writes gx (6); gate_add reads x, y, writes out (6), backward reads g, y, writes
+    dy (6)."""
+    from ttt_video_dit_b200 import transformer_layer as TLm
+    x = torch.randn(B, L, E, device=dev).to(torch.bfloat16).requires_grad_(True)
+    y = torch.randn(B, L, E, device=dev).to(torch.bfloat16).requires_grad_(True)
+    A = (1 + 0.1 * torch.randn(B, 2, E, device=dev)).requires_grad_(True)
+    C = (0.1 * torch.randn(B, 2, E, device=dev)).requires_grad_(True)
+    go = torch.randn(B, L, E, device=dev).to(torch.bfloat16)
+    n = x.numel()
+    for name, fwd, fb, bb in (("ln_affine", lambda: TLm.LnAffine.apply(x, A, C, 498, 1e-6), 4, 6),
+                              ("gate_add", lambda: TLm.GateAdd.apply(x, y, A, 498), 6, 6)):
+        with torch.no_grad():
+            ms_f = timeit(fwd)
+        def fwdbwd():
+            o = fwd()
+            o.backward(go)
+            x.grad = None; y.grad = None; A.grad = None; C.grad = None
+        ms_fb = timeit(fwdbwd)
+        ms_b = ms_fb - ms_f
+        print(json.dumps({"kernel": name, "shape": [B, L, E], "fwd_ms": ms_f, "fwd_GBps": fb * n / ms_f / 1e6,
+                          "fwd_frac_of_hbm_peak": fb * n / ms_f / 1e6 / peaks["hbm_gbs"], "bwd_ms": ms_b,
+                          "bwd_GBps": bb * n / ms_b / 1e6, "bwd_frac_of_hbm_peak": bb * n / ms_b / 1e6 / peaks["hbm_gbs"]}))
+
+
+def bench_prologue(T=18048, H=48, B=1):
+    """Attention prologue (csrc/attn_prologue.cu): q/k LayerNorm + RoPE, 8 bytes per element forward (read + write of q and k)
+    and 12 backward (x, dy in; dx out), vs the same math as eager torch ops (what local_attention ran before)."""
+    q = torch.randn(B, T, H, 64, device=dev).to(torch.bfloat16).requires_grad_(True)
+    k = torch.randn(B, T, H, 64, device=dev).to(torch.bfloat16).requires_grad_(True)
+    w = [torch.ones(64, device=dev, requires_grad=True), torch.zeros(64, device=dev, requires_grad=True),
+         torch.ones(64, device=dev, requires_grad=True), torch.zeros(64, device=dev, requires_grad=True)]
+    sin, cos = torch.rand(T, 64, device=dev), torch.rand(T, 64, device=dev)
+    go = torch.randn(B, T, H, 64, device=dev).to(torch.bfloat16)
+    f = lambda: attention.QKNormRope.apply(q, k, *w, sin, cos, 498, 1e-6)
+    with torch.no_grad():
+        ms_f = timeit(f)
+    def fb():
+        a, b_ = f()
+        torch.autograd.backward((a, b_), (go, go))
+        q.grad = None; k.grad = None
+    ms_fb = timeit(fb)
+    n = 2 * q.numel()
+
+    def eager():
+        outs = []
+        for x_, gw, gb in ((q, w[0], w[1]), (k, w[2], w[3])):
+            yv = F.layer_norm(x_, (64,), gw.to(x_.dtype), gb.to(x_.dtype), 1e-6)
+            c_, s_ = cos[:T - 498].to(yv.dtype)[None, :, None, :], sin[:T - 498].to(yv.dtype)[None, :, None, :]
+            v_ = yv[:, 498:]
+            r = v_.reshape(*v_.shape[:-1], 32, 2)
+            r = torch.stack((-r[..., 1], r[..., 0]), dim=-1).flatten(-2)
+            outs.append(torch.cat([yv[:, :498], v_ * c_ + r * s_], dim=1))
+        return outs
+    def eager_fb():
+        a, b_ = eager()
+        torch.autograd.backward((a, b_), (go, go))
+        q.grad = None; k.grad = None
+    ms_e = timeit(eager_fb)
+    print(json.dumps({"kernel": "qk_norm_rope (attention prologue)", "shape": [B, T, H, 64], "fwd_ms": ms_f, "fwd_GBps": 4 * n / ms_f / 1e6,
+                      "fwd_frac_of_hbm_peak": 4 * n / ms_f / 1e6 / peaks["hbm_gbs"], "fwd_bwd_ms": ms_fb,
+                      "bwd_frac_of_hbm_peak": 6 * n / (ms_fb - ms_f) / 1e6 / peaks["hbm_gbs"], "eager_torch_fwd_bwd_ms": ms_e}))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input", "output_norm", "block"]
+    which = sys.argv[1:] or ["attention", "attention_bwd", "linear", "gate", "process_input", "output_norm", "adaln", "prologue", "block"]
+    if "adaln" in which:
+        bench_adaln()
+    if "prologue" in which:
+        bench_prologue()
     if "block" in which:
         bench_block()
     if "output_norm" in which:
