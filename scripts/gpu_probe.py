@@ -28,19 +28,6 @@ for (B,H,NC,G) in [(1,1,1,1),(1,1,2,1),(1,2,4,2),(2,3,7,3),(1,4,33,16)]:
     print('fwd', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'per-step', per,
           'ck', [O.rel_err(a.cpu(), b) for a,b in zip(ck, rck)], 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
 """ % (ROOT, ROOT),
-    "fwd_half": """
-import os
-os.environ['TTT_B200_HALF_GELU'] = '1'
-import torch, sys
-sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
-from oracle import ttt_oracle as O
-from test_gpu_mlp_forward import run_forward, oracle_forward
-for (B,H,NC,G) in [(1,1,1,1),(1,2,4,2),(2,3,7,3),(1,4,33,16),(1,2,282,16)]:
-    d = O.make_inputs(B,H,NC,seed=10+NC)
-    qkve, out, ck, last = run_forward(d, G, want_last=True)
-    ref, rck, rlast = oracle_forward(qkve, d, G)
-    print('fwd_half', (B,H,NC,G), 'out', O.rel_err(out.float().cpu(), ref), 'last', [O.rel_err(a.cpu(), b) for a,b in zip(last, rlast)], flush=True)
-""" % (ROOT, ROOT),
     "timing": """
 import os
 os.environ['TTT_B200_LIB'] = os.environ.get('TTT_B200_TIMING_LIB', %r + '/ttt_video_dit_b200/lib/libttt_b200_dbg.so')

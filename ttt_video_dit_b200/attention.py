@@ -119,7 +119,7 @@ def local_attention(vid, text, P, num_heads, text_length, tokens_per_frame, num_
     """``_attn_forward`` (dit.py:163-211).  vid [B, Lv, E], text [B, Lt, E] bf16; P: dict with q/k/v/o ``.weight``/``.bias``
     and q_norm/k_norm ``.weight``/``.bias``; sin/cos: RoPE tables [(t h w), 64] (cogvideo/utils.py:388-425).
     ``impl``: "b200" = this repo's tcgen05 attention kernels (csrc/attn_fwd.cu, attn_bwd.cu); "library" = the library SDPA the
-    reference calls (a GPU library call, as the q/k/v/o GEMMs are -- measured 1.6x faster than our kernel on B200 today,
+    reference calls (a GPU library call, as the q/k/v/o GEMMs are -- measured 1.4x faster than our kernel on B200 today,
     which is why the integration patch leaves it in place)."""
     if impl not in ("b200", "library"):
         raise ValueError(impl)
