@@ -115,7 +115,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* lnb = lnw + 64;
   float* b2t = lnb + 64;      // b2 of W_t
   float* db2c = b2t + 64;     // d b2 carried (grad w.r.t. b2 after step t; updated in place during the iteration)
-  float* etas = db2c + 64;    // eta of step t
+  float* etas = db2c + 64;    // -eta of step t (every use multiplies by -eta)
   // Reductions over token rows / hidden lanes are laid out so that every shared-memory word has exactly ONE writer per
   // step (no atomics): fp32 addition is not associative, and an unordered pair of adds onto a running sum would make the
   // whole backward bit-irreproducible (d b2 feeds every earlier step).  Row halves (warp & 1) own separate accumulators.
@@ -271,7 +271,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float q1t = nq1;
     if (tid < 64) {
       b2t[tid] = nb2;
-      etas[tid] = __uint_as_float((uint32_t)neta << 16);
+      etas[tid] = -__uint_as_float((uint32_t)neta << 16);
       // merge the second row half of the previous step, then the Q-side contribution of step t (state after step t)
       db2c[tid] = (db2c[tid] + db2h[tid]) + nq2;
       db2h[tid] = 0.f;
@@ -315,19 +315,19 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ===== A2 [H]: Z1 -> X2 tile (sC), gelu', gelu''
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S1 : TM_S0);
+        const f32x2 B1 = pk2(b1t);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float v[32];
           tmem_ld32(src + 32 * c, reinterpret_cast<uint32_t*>(v));
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float x0, x1, a0, a1, c0, c1;
-            gelu3(v[i] + b1t, x0, a0, c0);
-            gelu3(v[i + 1] + b1t, x1, a1, c1);
-            v[i] = x0; v[i + 1] = x1;
-            g1p[16 * c + i / 2] = pack_bf16(a0, a1);
-            g2p[16 * c + i / 2] = pack_bf16(c0, c1);
+          for (int i = 0; i < 32; i += 2) {  // two tokens per instruction (FFMA2)
+            f32x2 x, a, e;
+            gelu3x2(add2(pk2(v[i], v[i + 1]), B1), x, a, e);
+            up2(x, v[i], v[i + 1]);
+            g1p[16 * c + i / 2] = pack_bf16(a);
+            g2p[16 * c + i / 2] = pack_bf16(e);
           }
           st_row32(sbase + sC, j, 4 * c, v);
         }
@@ -413,12 +413,12 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int q = 0; q < 4; ++q) { const float4 v = xA[q * 64 + trow]; s1 += v.x; s2 += v.y; }
         ln_s1 = s1; ln_s2 = s2;
-        const float eta = etas[trow];
+        const float neg_eta = etas[trow];
 #pragma unroll
         for (int f = 0; f < 16; ++f) z[f] = (fmaf(64.f, tg[f], -s1) - z[f] * s2) * (ln_rstd * (1.f / 64.f));  // gradZ2
         st_row16(sbase + SM_TT1, trow, 2 * cq, z);
 #pragma unroll
-        for (int f = 0; f < 16; ++f) tg[f] = -eta * z[f];
+        for (int f = 0; f < 16; ++f) tg[f] = neg_eta * z[f];
         st_row16(sbase + SM_TT2, trow, 2 * cq, tg);
         tmem_ld16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(tg));  // acc5
         tc_wait_ld();
@@ -427,7 +427,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int f = 0; f < 16; ++f) {
           const float a = tg[f] + db2c[c0 + f];
           e = fmaf(-z[f], a, e);
-          tg[f] = -eta * a;
+          tg[f] = neg_eta * a;
         }
         epart[cq * 64 + trow] = e;
         tmem_st16(tmem + lane_addr + TM_S3 + c0, reinterpret_cast<uint32_t*>(tg));
@@ -455,17 +455,19 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_ld32(tmem + lane_addr + TM_S1 + 32 * half, reinterpret_cast<uint32_t*>(raw));
           tc_wait_ld();
           float ep[32];
+          const f32x2 DB1 = pk2(db1r);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint32_t gp1 = g1p[16 * ch + i / 2], gp2 = g2p[16 * ch + i / 2];
-            const float et0 = etas[32 * ch + i], et1 = etas[32 * ch + i + 1];
-            const float gz0 = pre[i] * bf16_lo(gp1), gz1 = pre[i + 1] * bf16_hi(gp1);   // gradZ1
-            const float E0 = raw[i] + db1r, E1 = raw[i + 1] + db1r;
-            const float d0 = -et0 * E0, d1 = -et1 * E1;                                 // d gradZ1
-            ep[i] = gz0 * E0; ep[i + 1] = gz1 * E1;
-            g2p[16 * ch + i / 2] = pack_bf16(pre[i] * d0 * bf16_lo(gp2), pre[i + 1] * d1 * bf16_hi(gp2));  // term2
-            raw[i] = d0 * bf16_lo(gp1); raw[i + 1] = d1 * bf16_hi(gp1);                 // DG1
-            pre[i] = -et0 * gz0; pre[i + 1] = -et1 * gz1;                               // G1eta
+          for (int i = 0; i < 32; i += 2) {  // two tokens per instruction (FFMA2)
+            const f32x2 g1 = bf16x2_to_f32x2(g1p[16 * ch + i / 2]), g2 = bf16x2_to_f32x2(g2p[16 * ch + i / 2]);
+            const f32x2 net = *reinterpret_cast<const f32x2*>(&etas[32 * ch + i]);  // -eta of the two tokens
+            const f32x2 pr = pk2(pre[i], pre[i + 1]);
+            const f32x2 gz = mul2(pr, g1);                                  // gradZ1
+            const f32x2 E = add2(pk2(raw[i], raw[i + 1]), DB1);
+            const f32x2 d = mul2(net, E);                                   // d gradZ1
+            up2(mul2(gz, E), ep[i], ep[i + 1]);
+            g2p[16 * ch + i / 2] = pack_bf16(mul2(mul2(pr, d), g2));        // term2
+            up2(mul2(d, g1), raw[i], raw[i + 1]);                           // DG1
+            up2(mul2(net, gz), pre[i], pre[i + 1]);                         // G1eta
           }
           st_row32(sbase + sW1, j, 4 * ch, raw);
           st_row32(sbase + sC, j, 4 * ch, pre);
@@ -599,7 +601,7 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ===== A10 [H]: dZ1 = dX2 * gelu'(Z1) + term2 -> sB ; d b1 += sum dZ1
       {
         const uint32_t src = tmem + lane_addr + (half ? TM_S2 : TM_S1);
-        float acc = 0.f;
+        f32x2 acc2 = pk2(0.f);  // even / odd tokens
         float v[2][32];
         tmem_ld32(src, reinterpret_cast<uint32_t*>(v[0]));
         tmem_ld32(src + 32, reinterpret_cast<uint32_t*>(v[1]));
@@ -608,14 +610,13 @@ ttt_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const uint32_t gp1 = g1p[16 * c + i / 2], tp = g2p[16 * c + i / 2];
-            v[c][i] = fmaf(v[c][i], bf16_lo(gp1), bf16_lo(tp));
-            v[c][i + 1] = fmaf(v[c][i + 1], bf16_hi(gp1), bf16_hi(tp));
-            acc += v[c][i] + v[c][i + 1];
+            const f32x2 r = fma2(pk2(v[c][i], v[c][i + 1]), bf16x2_to_f32x2(g1p[16 * c + i / 2]), bf16x2_to_f32x2(g2p[16 * c + i / 2]));
+            up2(r, v[c][i], v[c][i + 1]);
+            acc2 = add2(acc2, r);
           }
           st_row32(sbase + sB, j, 4 * c, v[c]);
         }
-        db1r += acc;
+        db1r += lo2(acc2) + hi2(acc2);
       }
       mbar_wait(bar_w1r, ph_w1r); ph_w1r ^= 1;
       mbar_wait(bar_aux, ph_aux); ph_aux ^= 1;   // DG1 (sW1) and X2 (sC) are no longer read by any MMA
