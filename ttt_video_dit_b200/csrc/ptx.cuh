@@ -268,47 +268,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, 
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ----------------------------------------------------------------------------------------------- SW128 helpers
-// byte offset of 16-B chunk c (0..7) of row r in a SW128 row tile
-__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
-// fp16 operand tiles (forward-type GEMMs of the TTT-MLP scans: 11-bit mantissa instead of bf16's 8 -- the first mini-batch
-// of a sequence has a LayerNorm std of ~3e-3 and amplifies operand rounding by 1/std, DESIGN.md "operand format")
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float f16_lo(uint32_t v) {
-  float r;
-  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}" : "=f"(r) : "r"(v));
-  return r;
-}
-__device__ __forceinline__ float f16_hi(uint32_t v) {
-  float r;
-  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}" : "=f"(r) : "r"(v));
-  return r;
-}
-// a bf16 pair -> the same two values as an fp16 pair (exact for |x| in [6.1e-5, 65504]; smaller magnitudes keep 2^-24 steps)
-__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) { return pack_f16(bf16_lo(v), bf16_hi(v)); }
-// operand-format switch of the TTT-MLP forward-type kernels
-template <bool kF16> __device__ __forceinline__ uint32_t pack_op(float lo, float hi) { return kF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
-template <bool kF16> __device__ __forceinline__ float op_lo(uint32_t v) { return kF16 ? f16_lo(v) : bf16_lo(v); }
-template <bool kF16> __device__ __forceinline__ float op_hi(uint32_t v) { return kF16 ? f16_hi(v) : bf16_hi(v); }
-
-__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void ld_shared_v4(uint32_t saddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr) : "memory");
-}
 // ----------------------------------------------------------------------------------------------- packed fp32 pairs
 // FFMA2 / FMUL2 / FADD2 (PTX fma/mul/add .f32x2): two fp32 lanes per register pair and per instruction, each lane rounded
 // exactly like the scalar instruction.  The fma pipe accepts one warp instruction every 2 cycles per scheduler
@@ -344,6 +303,12 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {  // two fp32 bit patterns (e.g. straight out of tcgen05.ld)
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void up2u(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 // a packed bf16 pair -> packed fp32 pair (low half first)
 __device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t v) { return pk2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u)); }
 __device__ __forceinline__ uint32_t pack_bf16(f32x2 v) {
@@ -354,6 +319,49 @@ __device__ __forceinline__ uint32_t pack_bf16(f32x2 v) {
   return r;
 }
 
+// ----------------------------------------------------------------------------------------------- SW128 helpers
+// byte offset of 16-B chunk c (0..7) of row r in a SW128 row tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// fp16 operand tiles (forward-type GEMMs of the TTT-MLP scans: 11-bit mantissa instead of bf16's 8 -- the first mini-batch
+// of a sequence has a LayerNorm std of ~3e-3 and amplifies operand rounding by 1/std, DESIGN.md "operand format")
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float f16_hi(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+// a bf16 pair -> the same two values as an fp16 pair (exact for |x| in [6.1e-5, 65504]; smaller magnitudes keep 2^-24 steps)
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) { return pack_f16(bf16_lo(v), bf16_hi(v)); }
+// operand-format switch of the TTT-MLP forward-type kernels
+template <bool kF16> __device__ __forceinline__ uint32_t pack_op(float lo, float hi) { return kF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+template <bool kF16> __device__ __forceinline__ uint32_t pack_op(f32x2 v) { float a, b; up2(v, a, b); return pack_op<kF16>(a, b); }
+template <bool kF16> __device__ __forceinline__ f32x2 op_to_f32x2(uint32_t v) { return kF16 ? pk2(f16_lo(v), f16_hi(v)) : pk2(bf16_lo(v), bf16_hi(v)); }
+template <bool kF16> __device__ __forceinline__ float op_lo(uint32_t v) { return kF16 ? f16_lo(v) : bf16_lo(v); }
+template <bool kF16> __device__ __forceinline__ float op_hi(uint32_t v) { return kF16 ? f16_hi(v) : bf16_hi(v); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t saddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr) : "memory");
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

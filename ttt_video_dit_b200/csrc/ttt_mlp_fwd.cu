@@ -74,6 +74,28 @@ __device__ __forceinline__ float gelu_only(float z) {
   return fmaf(hz, t, hz);
 }
 
+// the same two functions on packed pairs (same operations, same order, two tokens per instruction; tanh stays scalar)
+__device__ __forceinline__ f32x2 tanh2(f32x2 u) {
+  float u0, u1;
+  up2(u, u0, u1);
+  return pk2(tanh_fast(u0), tanh_fast(u1));
+}
+__device__ __forceinline__ f32x2 gelu_and_grad2(f32x2 z, f32x2& grad) {
+  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
+  const f32x2 C0 = pk2(c0), HALF = pk2(0.5f);
+  const f32x2 z2 = mul2(z, z);
+  const f32x2 t = tanh2(mul2(z, fma2(pk2(c1), z2, C0)));
+  const f32x2 hz = mul2(HALF, z);
+  grad = fma2(mul2(hz, fma2(mul2(t, pk2(-1.0f)), t, pk2(1.0f))), fma2(pk2(3.0f * c1), z2, C0), fma2(HALF, t, HALF));
+  return fma2(hz, t, hz);
+}
+__device__ __forceinline__ f32x2 gelu_only2(f32x2 z) {
+  const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
+  const f32x2 t = tanh2(mul2(z, fma2(pk2(c1), mul2(z, z), pk2(c0))));
+  const f32x2 hz = mul2(pk2(0.5f), z);
+  return fma2(hz, t, hz);
+}
+
 struct FwdParams {
   const __nv_bfloat16* last_eta;  // [B,H,NC,64]
   const float* ln_w;              // [H,64]
@@ -275,19 +297,18 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t v[32];
         tmem_ld32(tsrc + 32 * c, v);
         tc_wait_ld();
+        const f32x2 B1 = pk2(b1r);
         if (c < 2) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float g0, g1;
-            float x0 = gelu_and_grad(__uint_as_float(v[i]) + b1r, g0);
-            float x1 = gelu_and_grad(__uint_as_float(v[i + 1]) + b1r, g1);
-            v[i] = __float_as_uint(x0);
-            v[i + 1] = __float_as_uint(x1);
-            gp[16 * c + i / 2] = pack_bf16(g0, g1);
+          for (int i = 0; i < 32; i += 2) {  // two tokens per instruction (FFMA2)
+            f32x2 g;
+            const f32x2 x = gelu_and_grad2(add2(pk2u(v[i], v[i + 1]), B1), g);
+            up2u(x, v[i], v[i + 1]);
+            gp[16 * c + i / 2] = pack_bf16(g);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_only(__uint_as_float(v[i]) + b1r));
+          for (int i = 0; i < 32; i += 2) up2u(gelu_only2(add2(pk2u(v[i], v[i + 1]), B1)), v[i], v[i + 1]);
         }
         store_row_op<kF16>(sbase + SM_X2 + (c >> 1) * 32768, j, 4 * (c & 1), v);
       }
@@ -319,29 +340,41 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int ch = warp >> 2;                // column half
       const bool kside = row < 64;
       const bool active = kside ? has_k : has_q;
-      float z[32];
+      // packed pairs of adjacent columns throughout (FFMA2); row sums are accumulated per lane of the pair (even / odd
+      // columns) and the two lanes added at the end
+      f32x2 z[16];
+      const f32x2* lw2 = reinterpret_cast<const f32x2*>(lnw + 32 * ch);
+      const f32x2* lb2 = reinterpret_cast<const f32x2*>(lnb + 32 * ch);
       float mu = 0.f, rstd = 0.f;
       if (active) {
-        tmem_ld32(tmem + lane_addr + TM_D2 + 32 * ch, reinterpret_cast<uint32_t*>(z));
+        uint32_t zr[32];
+        tmem_ld32(tmem + lane_addr + TM_D2 + 32 * ch, zr);
         tc_wait_ld();
-        float a1 = 0.f, a2 = 0.f;
+        const f32x2* b2p = reinterpret_cast<const f32x2*>(b2s + 32 * ch);
+        f32x2 a1 = pk2(0.f), a2 = pk2(0.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { z[i] += b2s[32 * ch + i]; a1 += z[i]; a2 = fmaf(z[i], z[i], a2); }
-        xs1[ch * 128 + row] = make_float2(a1, a2);
+        for (int i = 0; i < 16; ++i) {
+          z[i] = add2(pk2u(zr[2 * i], zr[2 * i + 1]), b2p[i]);
+          a1 = add2(a1, z[i]);
+          a2 = fma2(z[i], z[i], a2);
+        }
+        xs1[ch * 128 + row] = make_float2(lo2(a1) + hi2(a1), lo2(a2) + hi2(a2));
       }
       __syncthreads();
       if (active) {
         const float2 p0 = xs1[row], p1 = xs1[128 + row];
         mu = (p0.x + p1.x) * (1.0f / 64.0f);
         rstd = rsqrtf(fmaxf((p0.y + p1.y) * (1.0f / 64.0f) - mu * mu, 0.f) + 1e-8f);
+        const f32x2 MU = pk2(mu), RS = pk2(rstd);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) z[i] = (z[i] - mu) * rstd;  // x_hat
+        for (int i = 0; i < 16; ++i) z[i] = mul2(sub2(z[i], MU), RS);  // x_hat
       }
       if (kside) {
         // grad_out = gamma*xhat + beta - (V - K); gxh = grad_out*gamma        (K tile in operand format, V tile bf16)
         float g[32];
-        float s1 = 0.f, s2 = 0.f;
+        f32x2 gq[16];
         if (active) {
+          f32x2 s1 = pk2(0.f), s2 = pk2(0.f);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t kk[4], vv[4];
@@ -349,32 +382,31 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ld_shared_v4(vt + sw128_off(row, 4 * ch + c), vv[0], vv[1], vv[2], vv[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int i = 8 * c + 2 * e, f = 32 * ch + i;
-              const float t0 = bf16_lo(vv[e]) - op_lo<kF16>(kk[e]);
-              const float t1 = bf16_hi(vv[e]) - op_hi<kF16>(kk[e]);
-              g[i] = (fmaf(lnw[f], z[i], lnb[f]) - t0) * lnw[f];
-              g[i + 1] = (fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]) - t1) * lnw[f + 1];
-              s1 += g[i] + g[i + 1];
-              s2 = fmaf(g[i], z[i], s2);
-              s2 = fmaf(g[i + 1], z[i + 1], s2);
+              const int i = 4 * c + e;  // pair index: columns 32 ch + 2 i, + 1
+              const f32x2 tgt = sub2(bf16x2_to_f32x2(vv[e]), op_to_f32x2<kF16>(kk[e]));
+              gq[i] = mul2(sub2(fma2(lw2[i], z[i], lb2[i]), tgt), lw2[i]);
+              s1 = add2(s1, gq[i]);
+              s2 = fma2(gq[i], z[i], s2);
             }
           }
-          xs2[ch * 64 + row] = make_float2(s1, s2);
+          xs2[ch * 64 + row] = make_float2(lo2(s1) + hi2(s1), lo2(s2) + hi2(s2));
         }
         __syncthreads();
         if (active) {
           const float2 p0 = xs2[row], p1 = xs2[64 + row];
-          s1 = p0.x + p1.x; s2 = p0.y + p1.y;
+          const float s1 = p0.x + p1.x, s2 = p0.y + p1.y;
           // gradZ2 = (64*g - s1 - xhat*s2) / (64*std);  G2 = -eta * gradZ2
           const float eta_i = __uint_as_float((uint32_t)eta_raw << 16);
-          const float sc = -eta_i * rstd * (1.0f / 64.0f);
+          const f32x2 SC = pk2(-eta_i * rstd * (1.0f / 64.0f)), NS1 = pk2(-s1), S2 = pk2(s2), C64 = pk2(64.0f);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) g[i] = (fmaf(64.0f, g[i], -s1) - z[i] * s2) * sc;
+          for (int i = 0; i < 16; ++i) {
+            gq[i] = mul2(sub2(fma2(C64, gq[i], NS1), mul2(z[i], S2)), SC);
+            up2(gq[i], g[2 * i], g[2 * i + 1]);
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            st_shared_v4(sbase + SM_G2 + sw128_off(row, 4 * ch + c), pack_op<kF16>(g[8 * c], g[8 * c + 1]),
-                         pack_op<kF16>(g[8 * c + 2], g[8 * c + 3]), pack_op<kF16>(g[8 * c + 4], g[8 * c + 5]),
-                         pack_op<kF16>(g[8 * c + 6], g[8 * c + 7]));
+            st_shared_v4(sbase + SM_G2 + sw128_off(row, 4 * ch + c), pack_op<kF16>(gq[4 * c]), pack_op<kF16>(gq[4 * c + 1]),
+                         pack_op<kF16>(gq[4 * c + 2]), pack_op<kF16>(gq[4 * c + 3]));
           // b2 update = column sums of G2 over the 64 token rows (butterfly over the warp, then one shared add per row half:
           // db2acc starts at zero every step and takes exactly two addends, so the sum does not depend on their order)
 #pragma unroll
@@ -400,10 +432,8 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ld_shared_v4(kq + 8192 + sw128_off(r, 4 * ch + c), qq[0], qq[1], qq[2], qq[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int i = 8 * c + 2 * e, f = 32 * ch + i;
-              const float o0 = op_lo<kF16>(qq[e]) + fmaf(lnw[f], z[i], lnb[f]);
-              const float o1 = op_hi<kF16>(qq[e]) + fmaf(lnw[f + 1], z[i + 1], lnb[f + 1]);
-              o[e] = pack_bf16(o0, o1);
+              const int i = 4 * c + e;
+              o[e] = pack_bf16(add2(op_to_f32x2<kF16>(qq[e]), fma2(lw2[i], z[i], lb2[i])));
             }
             *reinterpret_cast<uint4*>(og + 8 * c) = make_uint4(o[0], o[1], o[2], o[3]);
           }
@@ -452,7 +482,7 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ---------------- P6: G1^T row j = D3 row j * gelu'(Z1) ; b1 += sum ; threads 0-63: b2 += column sums of G2
     {
       const uint32_t tsrc = tmem + lane_addr + TM_D3 + 128 * half;
-      float acc = 0.f;
+      f32x2 acc = pk2(0.f);  // even / odd tokens
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -460,16 +490,13 @@ ttt_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const uint32_t gpk = gp[16 * c + i / 2];
-          float a0 = __uint_as_float(v[i]) * bf16_lo(gpk);
-          float a1 = __uint_as_float(v[i + 1]) * bf16_hi(gpk);
-          acc += a0 + a1;
-          v[i] = __float_as_uint(a0);
-          v[i + 1] = __float_as_uint(a1);
+          const f32x2 a = mul2(pk2u(v[i], v[i + 1]), bf16x2_to_f32x2(gp[16 * c + i / 2]));
+          acc = add2(acc, a);
+          up2u(a, v[i], v[i + 1]);
         }
         store_row_op<kF16>(sbase + SM_X2 + 32768, j, 4 * c, v);
       }
-      b1r += acc;
+      b1r += lo2(acc) + hi2(acc);
       if (tid < 64) {  // fold the column sums of G2 gathered in P4 into b2
         b2s[tid] += db2acc[tid];
         db2acc[tid] = 0.f;
