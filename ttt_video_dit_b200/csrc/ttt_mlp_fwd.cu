@@ -56,6 +56,8 @@ constexpr uint32_t TM_D1 = 256;  // + 128*h ; cols [0,64) K side, [64,128) Q sid
 constexpr uint32_t TM_D3 = 256;  // + 128*h ; aliases the K side of D1
 constexpr uint32_t TM_D2 = 320;  // aliases the Q side of D1 half 0
 
+// Scalar definitions of the two activations (tanh-GELU, ops/utils.py:45-54).  The kernel runs the packed-pair forms below
+// (same operations in the same order on two tokens per instruction); these stay as the readable statement of the math.
 __device__ __forceinline__ float gelu_and_grad(float z, float& grad) {
   const float c0 = 0.79788456f, c1 = 0.79788456f * 0.044715f;
   float z2 = z * z;
