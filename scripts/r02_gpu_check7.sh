@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 N=${1:-8}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,memory.total --format=csv > gpurun_out/r02_${N}gpu_devices.txt
-( time timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $N --steps 5 --warmup 2 ) \
+( time timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $N --steps 5 --warmup 3 ) \
   > gpurun_out/r02_bench_${N}gpu_sharded.json 2> gpurun_out/r02_bench_${N}gpu_sharded.err
 echo "rc=$?"; grep -v "ProcessGroupNCCL\|Warning\|^$" gpurun_out/r02_bench_${N}gpu_sharded.err | tail -8
 python - <<PY
