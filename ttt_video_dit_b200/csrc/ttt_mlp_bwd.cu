@@ -1,15 +1,20 @@
 // TTT-MLP backward for sm_100a.  Replaces ttt-tk/kernels/ttt_backward/ttt.cu:179-1917 (bwd_ttt_mlp_ker / ttt_backward).
 //
 // Structure (differs from the reference on purpose, SURVEY 7 "Backward memory traffic"): per checkpoint group g, in
-// reverse order, two launches:
-//   1. trajectory  (ttt_mlp_fwd_kernel<true>, csrc/ttt_mlp_fwd.cu): re-runs the K side of the group's steps from the
-//      fp32 checkpoint and stores only the bf16 operand images of each state W_t (64 KB/step, L2 resident) -- the
-//      reference spills 16 intermediates per step (~338 KB/step);
-//   2. reverse     (this file): walks t = t_hi .. t_lo.  Iteration t uses ONE state image W_t for both the K side of
-//      step t (recompute + closed-form backward, SURVEY appendix B = ttt-tk/kernels/ttt_backward/matching.py:173-342)
-//      and the Q side of step t-1 (which only needs the state *after* step t-1, i.e. W_t).
-// dW1^T, dW2 (grad w.r.t. the carried state) are persistent fp32 TMEM accumulators; between launches they live in a
-// small fp32 scratch.  Same "hidden units on TMEM lanes" layout as the forward; all tiles use SW128 row tiles.
+// reverse order, three kernels on three streams:
+//   1. trajectory  (csrc/ttt_mlp_traj.cu): re-runs the K side of the group's steps from the fp32 checkpoint and stores only
+//      the bf16 operand images of each state W_t (64 KB/step) -- the reference spills 16 intermediates per step
+//      (~338 KB/step);
+//   2. Q side      (csrc/ttt_mlp_bwd_q.cu): the backward of the output half of every step, which does not depend on the
+//      carried state gradient: one CTA per (sequence, step) on the SMs the sequential kernels leave idle; emits dQ and
+//      the factor tiles of its contribution to dW1 / dW2;
+//   3. K side      (this file): the sequential chain.  Walks t = t_hi .. t_lo; iteration t recomputes the K side of step t
+//      from the image of W_t, applies the closed-form backward (SURVEY appendix B = ttt-tk/kernels/ttt_backward/
+//      matching.py:173-342) and adds the Q-side factor tiles of step t with two accumulate-MMAs.  In persistent mode one
+//      launch walks every group and hand-shakes with the other two kernels through device-side counters.
+// dW1^T, dW2 (grad w.r.t. the carried state) are persistent fp32 TMEM accumulators; between launches (per-group mode) they
+// live in a small fp32 scratch.  Same "hidden units on TMEM lanes" layout as the forward; all tiles are SW128 row tiles.
+// The hidden-lane element-wise phases use packed fp32 pairs (FFMA2, ptx.cuh); the token phases are scalar (measured).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
